@@ -1,0 +1,290 @@
+// layernorm.cu — fused (bias already added by the GEMM epilogue) LayerNorm + ReLU forward / backward over
+// expert-grouped rows, plus grouped column sums (bias gradients).
+//
+// Reference semantics: nn.LayerNorm(4h) -> nn.ReLU between the expert's Linear layers
+// (/root/reference/experiments/throughput/layers.py:9-15); per-expert affine parameters gamma/beta are stacked [G, C].
+//
+// Rows are grouped by expert in 128-row tiles; tile_group[t] gives the expert (or -1: tile unused, skipped).
+#include "sm100.cuh"
+
+namespace lah {
+
+constexpr float LN_EPS = 1e-5f;
+
+// ------------------------------------------------------------------------------------------------
+// forward: one warp per row, lane owns C/32 columns as chunks of 8 (coalesced 16B accesses)
+//   a = relu((h - mean) * rstd * gamma + beta);  saves mean / rstd per row
+// ------------------------------------------------------------------------------------------------
+template <int C>
+__global__ void __launch_bounds__(256) ln_relu_fwd_kernel(const bf16* __restrict__ h, bf16* __restrict__ a,
+                                                          float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                                          const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta,
+                                                          const int* __restrict__ tile_group, int rows, int relu) {
+    constexpr int NV = C / 256;  // int4 (8 x bf16) chunks per lane
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = blockIdx.x * 8 + warp;
+    if (row >= rows) return;
+    const int g = tile_group ? __ldg(tile_group + (row >> 7)) : 0;
+    if (g < 0) return;
+    const int4* hp = reinterpret_cast<const int4*>(h + static_cast<long long>(row) * C);
+    float v[NV * 8];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        const int4 q = ld_nc_v4(hp + j * 32 + lane);
+        const uint32_t w[4] = {(uint32_t)q.x, (uint32_t)q.y, (uint32_t)q.z, (uint32_t)q.w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const float2 f = unpack_bf16x2(w[t]);
+            v[j * 8 + 2 * t] = f.x;
+            v[j * 8 + 2 * t + 1] = f.y;
+            s += f.x + f.y;
+        }
+    }
+    const float mean = warp_sum(s) * (1.f / C);
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV * 8; ++i) {
+        const float d = v[i] - mean;
+        ss += d * d;
+    }
+    const float rstd = rsqrtf(warp_sum(ss) * (1.f / C) + LN_EPS);
+    if (lane == 0) {
+        mean_out[row] = mean;
+        rstd_out[row] = rstd;
+    }
+    const float* gp = gamma + static_cast<long long>(g) * C;
+    const float* bp = beta + static_cast<long long>(g) * C;
+    int4* ap = reinterpret_cast<int4*>(a + static_cast<long long>(row) * C);
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        const int col = (j * 32 + lane) * 8;
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gp + col));
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gp + col + 4));
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(bp + col));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(bp + col + 4));
+        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        float y[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            y[t] = (v[j * 8 + t] - mean) * rstd * gg[t] + bb[t];
+            if (relu) y[t] = fmaxf(y[t], 0.f);
+        }
+        int4 q;
+        q.x = pack_bf16x2(y[0], y[1]);
+        q.y = pack_bf16x2(y[2], y[3]);
+        q.z = pack_bf16x2(y[4], y[5]);
+        q.w = pack_bf16x2(y[6], y[7]);
+        ap[j * 32 + lane] = q;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward: one CTA (C/8 threads) per 128-row tile; thread owns 8 consecutive columns, keeps fp32 column
+// accumulators (dgamma, dbeta, dbias) in registers for the whole tile, block-reduces the two row statistics.
+//   y    = xhat*gamma + beta            (recomputed; relu mask = y > 0)
+//   g    = da * mask                    dbeta += g        dgamma += g * xhat
+//   dxh  = g * gamma
+//   dh   = rstd * (dxh - mean_c(dxh) - xhat * mean_c(dxh * xhat))     dbias += dh
+// ------------------------------------------------------------------------------------------------
+template <int C>
+__global__ void __launch_bounds__(C / 8) ln_relu_bwd_kernel(const bf16* __restrict__ da, const bf16* __restrict__ h,
+                                                            const float* __restrict__ mean_in,
+                                                            const float* __restrict__ rstd_in,
+                                                            const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, bf16* __restrict__ dh,
+                                                            float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                            float* __restrict__ dbias,
+                                                            const int* __restrict__ tile_group, int rows, int relu) {
+    constexpr int THREADS = C / 8;
+    constexpr int WARPS = THREADS / 32;
+    constexpr int RB = (C >= 4096) ? 2 : 4;  // rows per batch (register blocking)
+    __shared__ float red[WARPS][2 * RB];
+    __shared__ float tot[2 * RB];
+    const int tile = blockIdx.x;
+    const int g = tile_group ? __ldg(tile_group + tile) : 0;
+    if (g < 0) return;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int col = tid * 8;
+    float gam[8], bet[8];
+    {
+        const float* gp = gamma + static_cast<long long>(g) * C + col;
+        const float* bp = beta + static_cast<long long>(g) * C + col;
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gp)), g1 = __ldg(reinterpret_cast<const float4*>(gp + 4));
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(bp)), b1 = __ldg(reinterpret_cast<const float4*>(bp + 4));
+        gam[0] = g0.x; gam[1] = g0.y; gam[2] = g0.z; gam[3] = g0.w; gam[4] = g1.x; gam[5] = g1.y; gam[6] = g1.z; gam[7] = g1.w;
+        bet[0] = b0.x; bet[1] = b0.y; bet[2] = b0.z; bet[3] = b0.w; bet[4] = b1.x; bet[5] = b1.y; bet[6] = b1.z; bet[7] = b1.w;
+    }
+    float acc_dg[8], acc_db[8], acc_dbias[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) acc_dg[t] = acc_db[t] = acc_dbias[t] = 0.f;
+
+    const int row0 = tile * 128;
+    const int row_end = min(rows, row0 + 128);
+    for (int rb = row0; rb < row_end; rb += RB) {
+        float gv[RB][8], xh[RB][8], rs[RB];
+        float part[2 * RB];
+#pragma unroll
+        for (int r = 0; r < RB; ++r) {
+            const int row = rb + r;
+            const bool ok = row < row_end;
+            const long long off = static_cast<long long>(ok ? row : row0) * C + col;
+            const int4 qa = ld_nc_v4(reinterpret_cast<const int4*>(da + off));
+            const int4 qh = ld_nc_v4(reinterpret_cast<const int4*>(h + off));
+            const float mu = __ldg(mean_in + (ok ? row : row0));
+            rs[r] = __ldg(rstd_in + (ok ? row : row0));
+            const uint32_t wa[4] = {(uint32_t)qa.x, (uint32_t)qa.y, (uint32_t)qa.z, (uint32_t)qa.w};
+            const uint32_t wh[4] = {(uint32_t)qh.x, (uint32_t)qh.y, (uint32_t)qh.z, (uint32_t)qh.w};
+            float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const float2 fa = unpack_bf16x2(wa[t]);
+                const float2 fh = unpack_bf16x2(wh[t]);
+                const float x0 = (fh.x - mu) * rs[r], x1 = (fh.y - mu) * rs[r];
+                const float y0 = x0 * gam[2 * t] + bet[2 * t], y1 = x1 * gam[2 * t + 1] + bet[2 * t + 1];
+                const float g0 = (ok && (!relu || y0 > 0.f)) ? fa.x : 0.f;
+                const float g1 = (ok && (!relu || y1 > 0.f)) ? fa.y : 0.f;
+                gv[r][2 * t] = g0; gv[r][2 * t + 1] = g1;
+                xh[r][2 * t] = x0; xh[r][2 * t + 1] = x1;
+                const float d0 = g0 * gam[2 * t], d1 = g1 * gam[2 * t + 1];
+                s1 += d0 + d1;
+                s2 += d0 * x0 + d1 * x1;
+            }
+            part[2 * r] = s1;
+            part[2 * r + 1] = s2;
+        }
+#pragma unroll
+        for (int i = 0; i < 2 * RB; ++i) part[i] = warp_sum(part[i]);
+        if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < 2 * RB; ++i) red[warp][i] = part[i];
+        }
+        __syncthreads();
+        if (tid < 2 * RB) {
+            float s = 0.f;
+#pragma unroll
+            for (int w = 0; w < WARPS; ++w) s += red[w][tid];
+            tot[tid] = s * (1.f / C);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < RB; ++r) {
+            const int row = rb + r;
+            if (row >= row_end) continue;
+            const float m1 = tot[2 * r], m2 = tot[2 * r + 1];
+            float o[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                o[t] = rs[r] * (gv[r][t] * gam[t] - m1 - xh[r][t] * m2);
+                acc_db[t] += gv[r][t];
+                acc_dg[t] += gv[r][t] * xh[r][t];
+                acc_dbias[t] += o[t];
+            }
+            int4 q;
+            q.x = pack_bf16x2(o[0], o[1]);
+            q.y = pack_bf16x2(o[2], o[3]);
+            q.z = pack_bf16x2(o[4], o[5]);
+            q.w = pack_bf16x2(o[6], o[7]);
+            *reinterpret_cast<int4*>(dh + static_cast<long long>(row) * C + col) = q;
+        }
+        // `tot` is rewritten only after the next batch's first __syncthreads, which every thread reaches
+        // after it finished reading tot above -> no extra barrier needed.
+    }
+    float* pg = dgamma + static_cast<long long>(g) * C + col;
+    float* pb = dbeta + static_cast<long long>(g) * C + col;
+    float* pbi = dbias + static_cast<long long>(g) * C + col;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+        atomicAdd(pg + t, acc_dg[t]);
+        atomicAdd(pb + t, acc_db[t]);
+        atomicAdd(pbi + t, acc_dbias[t]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// grouped column sum: out[g, c] += sum over the rows of every 128-row tile of group g of x[row, c]
+// CTA = (tile, 256-column slab); thread owns one column pair, 4 row phases
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512) grouped_colsum_kernel(const bf16* __restrict__ x, long long ldx,
+                                                             float* __restrict__ out, int C,
+                                                             const int* __restrict__ tile_group, int rows) {
+    __shared__ float2 sm[4][128];
+    const int tile = blockIdx.x;
+    const int g = tile_group ? __ldg(tile_group + tile) : 0;
+    if (g < 0) return;
+    const int cp = threadIdx.x & 127;         // column pair inside the slab
+    const int phase = threadIdx.x >> 7;       // 0..3
+    const int col = blockIdx.y * 256 + cp * 2;
+    if (col >= C) return;                      // C is a multiple of 256 in practice; whole warps exit together
+    const int row0 = tile * 128, row_end = min(rows, row0 + 128);
+    float2 acc = make_float2(0.f, 0.f);
+    for (int r = row0 + phase; r < row_end; r += 4) {
+        const uint32_t u = __ldg(reinterpret_cast<const uint32_t*>(x + static_cast<long long>(r) * ldx + col));
+        const float2 f = unpack_bf16x2(u);
+        acc.x += f.x;
+        acc.y += f.y;
+    }
+    sm[phase][cp] = acc;
+    __syncthreads();
+    if (phase == 0) {
+        float2 s = sm[0][cp];
+#pragma unroll
+        for (int p = 1; p < 4; ++p) {
+            s.x += sm[p][cp].x;
+            s.y += sm[p][cp].y;
+        }
+        atomicAdd(out + static_cast<long long>(g) * C + col, s.x);
+        atomicAdd(out + static_cast<long long>(g) * C + col + 1, s.y);
+    }
+}
+
+}  // namespace lah
+
+using namespace lah;
+
+extern "C" {
+
+int lah_ln_relu_fwd(const void* h, void* a, float* mean, float* rstd, const float* gamma, const float* beta,
+                    const int* tile_group, int rows, int C, int relu, cudaStream_t st) {
+    if (rows <= 0) return 0;
+    const int grid = (rows + 7) / 8;
+#define LAH_LN_FWD(CC)                                                                                          \
+    if (C == CC) {                                                                                              \
+        ln_relu_fwd_kernel<CC><<<grid, 256, 0, st>>>((const bf16*)h, (bf16*)a, mean, rstd, gamma, beta,         \
+                                                     tile_group, rows, relu);                                   \
+        return -(int)cudaGetLastError();                                                                        \
+    }
+    LAH_LN_FWD(256) LAH_LN_FWD(512) LAH_LN_FWD(1024) LAH_LN_FWD(2048) LAH_LN_FWD(4096)
+#undef LAH_LN_FWD
+    return -2;
+}
+
+int lah_ln_relu_bwd(const void* da, const void* h, const float* mean, const float* rstd, const float* gamma,
+                    const float* beta, void* dh, float* dgamma, float* dbeta, float* dbias, const int* tile_group,
+                    int rows, int C, int relu, cudaStream_t st) {
+    if (rows <= 0) return 0;
+    const int grid = (rows + 127) / 128;
+#define LAH_LN_BWD(CC)                                                                                          \
+    if (C == CC) {                                                                                              \
+        ln_relu_bwd_kernel<CC><<<grid, CC / 8, 0, st>>>((const bf16*)da, (const bf16*)h, mean, rstd, gamma,    \
+                                                        beta, (bf16*)dh, dgamma, dbeta, dbias, tile_group,     \
+                                                        rows, relu);                                            \
+        return -(int)cudaGetLastError();                                                                        \
+    }
+    LAH_LN_BWD(256) LAH_LN_BWD(512) LAH_LN_BWD(1024) LAH_LN_BWD(2048) LAH_LN_BWD(4096)
+#undef LAH_LN_BWD
+    return -2;
+}
+
+int lah_grouped_colsum(const void* x, long long ldx, float* out, int C, const int* tile_group, int rows,
+                       cudaStream_t st) {
+    if (rows <= 0) return 0;
+    if (C % 256) return -2;
+    dim3 grid((rows + 127) / 128, (C + 255) / 256);
+    grouped_colsum_kernel<<<grid, 512, 0, st>>>((const bf16*)x, ldx, out, C, tile_group, rows);
+    return -(int)cudaGetLastError();
+}
+
+}  // extern "C"

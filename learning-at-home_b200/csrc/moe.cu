@@ -1,0 +1,661 @@
+// moe.cu — DMoE routing + expert all-to-all as peer-to-peer (NVLink/NVSwitch) kernels.
+//
+// What the reference does with Python threads, a Kademlia DHT and one blocking TCP RPC per (sample, expert)
+// (/root/reference/lib/client/gating_function.py:25-153, lib/client/remote_expert.py:53-76,
+//  lib/runtime/task_pool.py:141-172) is done here by five kernels operating on SYMMETRIC buffers (same offset on every
+// GPU, every GPU's heap mapped into every peer):
+//
+//   gate_topk        product-key scores + liveness table + Bernoulli failure injection -> exact top-k, softmax over the
+//                    survivors, per-expert slot allocation (the TaskPool "batch assembly" becomes an atomic counter)
+//   layout_exchange  every rank stores its per-expert counts into every peer (P2P st), release/acquire flags, then each
+//                    rank derives the SAME global layout: rows grouped by expert, groups padded to 128 rows
+//   scatter_rows     fused permute + P2P store of token rows into the owner GPU's receive buffer (+ zero padding rows)
+//   combine_rows     weighted un-permute: P2P loads of expert outputs from the owners, softmax-weighted sum
+//   bwd_dispatch     d(weights) = <grad, expert_out> (P2P load), push w*grad to the owners (P2P store),
+//                    softmax backward -> gradient w.r.t. the grid logits
+//
+// Memory ordering protocol: data is written with plain stores, then `__threadfence_system()` +
+// `st.release.sys` of a monotonically increasing epoch into the consumer's flag word; consumers poll with
+// `ld.acquire.sys`.  Flags never need resetting.  Every poll loop has a clock64() timeout that raises status[0].
+#include "sm100.cuh"
+
+namespace lah {
+
+constexpr int MAX_WORLD = 8;
+constexpr int MAX_GRID_DIMS = 4;
+constexpr int MAX_K = 8;
+constexpr long long SPIN_TIMEOUT_CYCLES = 20000000000ll;  // ~10 s
+
+struct Peers {
+    char* base[MAX_WORLD];  // base of every rank's symmetric heap, as mapped in THIS process
+    int world;
+    int me;
+};
+
+struct GridSpec {
+    int ndim;
+    int size[MAX_GRID_DIMS];    // grid_size
+    int offset[MAX_GRID_DIMS];  // offset of the dim's logits inside a logits row
+    int total;                  // sum(size)
+    int num_experts;            // prod(size)
+};
+
+enum Status { STATUS_TIMEOUT = 1, STATUS_OVERFLOW = 2 };
+
+__device__ __forceinline__ float hash_uniform(unsigned long long x) {
+    // splitmix64 -> uniform in [0, 1)
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    x = x ^ (x >> 31);
+    return static_cast<float>(x >> 40) * (1.0f / 16777216.0f);
+}
+
+__device__ __forceinline__ bool spin_until_ge(const int* flag, int epoch, int* status) {
+    const long long t0 = clock64();
+    while (ld_acquire_sys(flag) < epoch) {
+        if (clock64() - t0 > SPIN_TIMEOUT_CYCLES) {
+            atomicOr(status, STATUS_TIMEOUT);
+            return false;
+        }
+    }
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// gate: one warp per token
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gate_topk_kernel(const float* __restrict__ logits, int B, GridSpec gs, int k,
+                                                        const unsigned char* __restrict__ alive, float failure_rate,
+                                                        unsigned long long seed, long long token_offset,
+                                                        int* __restrict__ idx_out, float* __restrict__ w_out,
+                                                        int* __restrict__ pos_out, int* __restrict__ counts) {
+    extern __shared__ float s_logits[];  // [8 warps][gs.total]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * 8 + warp;
+    if (b >= B) return;
+    float* lg = s_logits + warp * gs.total;
+    for (int i = lane; i < gs.total; i += 32) lg[i] = logits[static_cast<long long>(b) * gs.total + i];
+    __syncwarp();
+
+    // per-lane sorted top-k over the candidates this lane owns (c = lane, lane+32, ...)
+    float best_v[MAX_K];
+    int best_i[MAX_K];
+#pragma unroll
+    for (int j = 0; j < MAX_K; ++j) {
+        best_v[j] = -INFINITY;
+        best_i[j] = -1;
+    }
+    for (int c = lane; c < gs.num_experts; c += 32) {
+        if (alive && !alive[c]) continue;
+        if (failure_rate > 0.f) {
+            const unsigned long long key = seed ^ (static_cast<unsigned long long>(token_offset + b) * 0x100000001B3ull +
+                                                   static_cast<unsigned long long>(c));
+            if (hash_uniform(key) < failure_rate) continue;
+        }
+        int rem = c;
+        float s = 0.f;
+#pragma unroll
+        for (int d = MAX_GRID_DIMS - 1; d >= 0; --d) {
+            if (d < gs.ndim) {
+                const int i = rem % gs.size[d];
+                rem /= gs.size[d];
+                s += lg[gs.offset[d] + i];
+            }
+        }
+        // insertion (ties keep the smaller expert id first because candidates arrive in increasing order)
+        if (s > best_v[MAX_K - 1] || best_i[MAX_K - 1] < 0) {
+            float v = s;
+            int id = c;
+            bool shifting = false;  // once inserted, everything below shifts down by one
+#pragma unroll
+            for (int j = 0; j < MAX_K; ++j) {
+                const bool take = shifting || (best_i[j] < 0) || (v > best_v[j]);
+                if (take) {
+                    shifting = true;
+                    const float tv = best_v[j];
+                    const int ti = best_i[j];
+                    best_v[j] = v;
+                    best_i[j] = id;
+                    v = tv;
+                    id = ti;
+                }
+            }
+        }
+    }
+    // merge: k rounds of warp arg-max over the heads of the per-lane lists
+    float sel_v[MAX_K];
+    int sel_i[MAX_K];
+    int head = 0;
+#pragma unroll
+    for (int j = 0; j < MAX_K; ++j) {
+        sel_v[j] = -INFINITY;
+        sel_i[j] = -1;
+        if (j < k) {
+            float v = -INFINITY;
+            int id = -1;
+#pragma unroll
+            for (int t = 0; t < MAX_K; ++t)
+                if (t == head) {
+                    v = best_v[t];
+                    id = best_i[t];
+                }
+            float bv = v;
+            int bi = id;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                const bool better = (oi >= 0) && (bi < 0 || ov > bv || (ov == bv && oi < bi));
+                if (better) {
+                    bv = ov;
+                    bi = oi;
+                }
+            }
+            sel_v[j] = bv;
+            sel_i[j] = bi;
+            if (bi >= 0 && bi == id) ++head;  // the winning lane pops its head
+        }
+    }
+    // softmax over the selected (alive) experts
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < MAX_K; ++j)
+        if (sel_i[j] >= 0) mx = fmaxf(mx, sel_v[j]);
+    float denom = 0.f;
+#pragma unroll
+    for (int j = 0; j < MAX_K; ++j)
+        if (sel_i[j] >= 0) denom += __expf(sel_v[j] - mx);
+    if (lane < k) {
+        int id = -1;
+        float v = 0.f;
+#pragma unroll
+        for (int j = 0; j < MAX_K; ++j)
+            if (j == lane) {
+                id = sel_i[j];
+                v = sel_v[j];
+            }
+        const long long o = static_cast<long long>(b) * k + lane;
+        idx_out[o] = id;
+        w_out[o] = id >= 0 ? __expf(v - mx) / denom : 0.f;
+        pos_out[o] = id >= 0 ? atomicAdd(counts + id, 1) : 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// layout exchange: single CTA of 1024 threads
+// ------------------------------------------------------------------------------------------------
+struct LayoutArgs {
+    long long cnt_all_off;   // symmetric int [MAX_WORLD][E]
+    long long flags_off;     // symmetric int [slots][MAX_WORLD]
+    int slot;
+    int epoch;
+    int E, E_loc;
+    int max_rows;            // capacity of the receive buffers (rows)
+    int max_tiles;           // max_rows / 128
+    int* counts;             // [E] local counts (zeroed on exit)
+    int* dst_row;            // [E]  row in the owner's buffer where MY first row for expert e goes
+    int* group_off;          // [E_loc + 1] padded offsets of my local experts
+    int* group_rows;         // [E_loc] valid rows of my local experts
+    int* tile_group;         // [max_tiles]
+    int* total_rows;         // [1] padded rows in my buffer
+    int* status;
+};
+
+__global__ void __launch_bounds__(1024) layout_exchange_kernel(Peers peers, LayoutArgs a) {
+    __shared__ int warp_tot[32];
+    __shared__ int owner_base_s[MAX_WORLD + 1];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int me = peers.me, world = peers.world;
+    // 1. publish my counts to every peer (plain P2P stores), then release the epoch flag on every peer
+    for (int r = 0; r < world; ++r) {
+        int* dst = reinterpret_cast<int*>(peers.base[r] + a.cnt_all_off) + static_cast<long long>(me) * a.E;
+        for (int e = tid; e < a.E; e += blockDim.x) dst[e] = a.counts[e];
+    }
+    __syncthreads();
+    if (tid < world) {
+        __threadfence_system();
+        int* f = reinterpret_cast<int*>(peers.base[tid] + a.flags_off) + a.slot * MAX_WORLD + me;
+        st_release_sys(f, a.epoch);
+        // 2. wait for everybody's counts
+        const int* fw = reinterpret_cast<const int*>(peers.base[me] + a.flags_off) + a.slot * MAX_WORLD + tid;
+        spin_until_ge(fw, a.epoch, a.status);
+    }
+    for (int t = tid; t < a.max_tiles; t += blockDim.x) a.tile_group[t] = -1;
+    __syncthreads();
+    // 3. global layout, computed redundantly (and identically) on every rank:
+    //    dst_row[e] <- exclusive prefix of padded group sizes over ALL experts (temporarily),
+    //    counts[e]  <- rows of expert e that come from ranks < me (the local counts are consumed by now)
+    const int* cnt_all = reinterpret_cast<const int*>(peers.base[me] + a.cnt_all_off);
+    int running = 0;
+    for (int chunk = 0; chunk < a.E; chunk += blockDim.x) {
+        const int e = chunk + tid;
+        int tot = 0, before = 0;
+        if (e < a.E) {
+            for (int s = 0; s < world; ++s) {
+                const int c = cnt_all[static_cast<long long>(s) * a.E + e];
+                tot += c;
+                if (s < me) before += c;
+            }
+        }
+        const int padded = (tot + 127) & ~127;
+        int v = padded;  // inclusive scan inside the warp
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int n = __shfl_up_sync(0xffffffffu, v, o);
+            if (lane >= o) v += n;
+        }
+        if (lane == 31) warp_tot[warp] = v;
+        __syncthreads();
+        if (warp == 0) {
+            int w = warp_tot[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int n = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += n;
+            }
+            warp_tot[lane] = w;
+        }
+        __syncthreads();
+        const int excl = running + (warp > 0 ? warp_tot[warp - 1] : 0) + v - padded;
+        running += warp_tot[31];
+        if (e < a.E) {
+            a.dst_row[e] = excl;
+            a.counts[e] = before;
+            if (e / a.E_loc == me) a.group_rows[e - me * a.E_loc] = tot;
+        }
+        __syncthreads();
+    }
+    if (tid < world) owner_base_s[tid] = a.dst_row[tid * a.E_loc];
+    if (tid == 0) owner_base_s[world] = running;
+    __syncthreads();
+    // 4. make offsets owner-relative; fill the tables of my local experts
+    for (int e = tid; e < a.E; e += blockDim.x) {
+        const int owner = e / a.E_loc;
+        const int rel = a.dst_row[e] - owner_base_s[owner];
+        const int before = a.counts[e];
+        a.counts[e] = 0;  // leave the slot counters clean for the next gate call
+        if (owner == me) {
+            const int le = e - me * a.E_loc;
+            a.group_off[le] = rel;
+            const int padded = (a.group_rows[le] + 127) & ~127;
+            for (int t = rel / 128; t < (rel + padded) / 128 && t < a.max_tiles; ++t) a.tile_group[t] = le;
+        }
+        a.dst_row[e] = rel + before;
+    }
+    if (tid == 0) {
+        const int total = owner_base_s[me + 1] - owner_base_s[me];
+        a.group_off[a.E_loc] = total;
+        *a.total_rows = total;
+        bool overflow = false;
+        for (int r = 0; r < world; ++r) overflow |= (owner_base_s[r + 1] - owner_base_s[r]) > a.max_rows;
+        if (overflow) atomicOr(a.status, STATUS_OVERFLOW);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// scatter: warp per (token, slot) pair -> P2P store of the row; extra CTAs zero the padding rows of local experts;
+// the last CTA to finish releases the epoch flag on every peer.
+// ------------------------------------------------------------------------------------------------
+struct ScatterArgs {
+    const bf16* src;          // [B, H] rows to send (x in forward, grad in backward)
+    const float* scale;       // [B*k] optional per-pair scale (backward: gate weights) or nullptr
+    const int* idx;           // [B*k] expert ids
+    const int* pos;           // [B*k] slot inside (me, expert)
+    const int* dst_row;       // [E]
+    int* pair_row;            // [B*k] out: row in the owner's buffer (or -1); nullptr in backward (rows known)
+    long long dst_off;        // symmetric receive buffer [max_rows, H] bf16
+    long long flags_off;
+    int slot, epoch;
+    int num_pairs, k, H, E_loc, max_rows;
+    const int* group_off;     // local experts (for zero padding)
+    const int* group_rows;
+    int pair_blocks;          // CTAs that handle pairs; the rest zero padding
+    int* done_counter;
+    int* status;
+};
+
+template <int VEC_PER_LANE>
+__global__ void __launch_bounds__(256) scatter_rows_kernel(Peers peers, ScatterArgs a) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (static_cast<int>(blockIdx.x) < a.pair_blocks) {
+        const int p = blockIdx.x * 8 + warp;
+        if (p < a.num_pairs) {
+            const int e = a.idx[p];
+            int row = -1;
+            if (e >= 0) {
+                row = (a.pair_row && !a.dst_row) ? a.pair_row[p] : a.dst_row[e] + a.pos[p];
+                if (row >= a.max_rows) {
+                    if (lane == 0) atomicOr(a.status, STATUS_OVERFLOW);
+                    row = -1;
+                }
+            }
+            if (a.pair_row && a.dst_row && lane == 0) a.pair_row[p] = row;
+            if (row >= 0) {
+                const int owner = e / a.E_loc;
+                const int b = p / a.k;
+                const int4* sp = reinterpret_cast<const int4*>(a.src + static_cast<long long>(b) * a.H);
+                int4* dp = reinterpret_cast<int4*>(peers.base[owner] + a.dst_off) +
+                           static_cast<long long>(row) * (a.H / 8);
+                int4 v[VEC_PER_LANE];
+#pragma unroll
+                for (int j = 0; j < VEC_PER_LANE; ++j) v[j] = ld_nc_v4(sp + j * 32 + lane);
+                if (a.scale) {
+                    const float s = a.scale[p];
+#pragma unroll
+                    for (int j = 0; j < VEC_PER_LANE; ++j) {
+                        uint32_t* u = reinterpret_cast<uint32_t*>(&v[j]);
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) {
+                            const float2 f = unpack_bf16x2(u[t]);
+                            u[t] = pack_bf16x2(f.x * s, f.y * s);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < VEC_PER_LANE; ++j) st_v4(dp + j * 32 + lane, v[j]);
+            }
+        }
+    } else {
+        // zero the padding rows of my local experts (rows [off+rows, next off))
+        const int nb = gridDim.x - a.pair_blocks;
+        int4* base = reinterpret_cast<int4*>(peers.base[peers.me] + a.dst_off);
+        const int4 z = make_int4(0, 0, 0, 0);
+        for (int le = blockIdx.x - a.pair_blocks; le < a.E_loc; le += nb) {
+            const int r0 = a.group_off[le] + a.group_rows[le];
+            const int r1 = min(a.max_rows, (a.group_off[le] + ((a.group_rows[le] + 127) & ~127)));
+            for (int r = r0 + warp; r < r1; r += 8) {
+                int4* dp = base + static_cast<long long>(r) * (a.H / 8);
+#pragma unroll
+                for (int j = 0; j < VEC_PER_LANE; ++j) dp[j * 32 + lane] = z;
+            }
+        }
+    }
+    // completion: last CTA publishes the epoch to every peer
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        const int prev = atomicAdd(a.done_counter, 1);
+        if (prev == static_cast<int>(gridDim.x) - 1) {
+            *a.done_counter = 0;
+            __threadfence_system();
+            for (int r = 0; r < peers.world; ++r) {
+                int* f = reinterpret_cast<int*>(peers.base[r] + a.flags_off) + a.slot * MAX_WORLD + peers.me;
+                st_release_sys(f, a.epoch);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// flag helpers: signal every peer / wait for every peer (single warp)
+// ------------------------------------------------------------------------------------------------
+__global__ void signal_wait_kernel(Peers peers, long long flags_off, int slot, int epoch, int do_signal, int do_wait,
+                                   int* status) {
+    const int lane = threadIdx.x;
+    if (do_signal && lane < peers.world) {
+        __threadfence_system();
+        int* f = reinterpret_cast<int*>(peers.base[lane] + flags_off) + slot * MAX_WORLD + peers.me;
+        st_release_sys(f, epoch);
+    }
+    if (do_wait && lane < peers.world) {
+        const int* f = reinterpret_cast<const int*>(peers.base[peers.me] + flags_off) + slot * MAX_WORLD + lane;
+        spin_until_ge(f, epoch, status);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// combine: warp per token; out[b] = sum_j w[b,j] * src_owner(j)[row(b,j)]     (w == nullptr -> plain sum)
+// ------------------------------------------------------------------------------------------------
+struct CombineArgs {
+    long long src_off;        // symmetric [max_rows, H] bf16 on the owners
+    const int* idx;           // [B*k]
+    const int* pair_row;      // [B*k]
+    const float* w;           // [B*k] or nullptr
+    bf16* out;                // [B, H]
+    int B, k, H, E_loc;
+};
+
+template <int VEC_PER_LANE>
+__global__ void __launch_bounds__(256) combine_rows_kernel(Peers peers, CombineArgs a) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * 8 + warp;
+    if (b >= a.B) return;
+    float acc[VEC_PER_LANE * 8];
+#pragma unroll
+    for (int i = 0; i < VEC_PER_LANE * 8; ++i) acc[i] = 0.f;
+    for (int j = 0; j < a.k; ++j) {
+        const long long p = static_cast<long long>(b) * a.k + j;
+        const int e = a.idx[p];
+        const int row = a.pair_row[p];
+        if (e < 0 || row < 0) continue;
+        const float w = a.w ? a.w[p] : 1.f;
+        const int4* sp = reinterpret_cast<const int4*>(peers.base[e / a.E_loc] + a.src_off) +
+                         static_cast<long long>(row) * (a.H / 8);
+#pragma unroll
+        for (int v = 0; v < VEC_PER_LANE; ++v) {
+            const int4 q = ld_v4(sp + v * 32 + lane);
+            const uint32_t u[4] = {(uint32_t)q.x, (uint32_t)q.y, (uint32_t)q.z, (uint32_t)q.w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const float2 f = unpack_bf16x2(u[t]);
+                acc[v * 8 + 2 * t] += w * f.x;
+                acc[v * 8 + 2 * t + 1] += w * f.y;
+            }
+        }
+    }
+    int4* op = reinterpret_cast<int4*>(a.out + static_cast<long long>(b) * a.H);
+#pragma unroll
+    for (int v = 0; v < VEC_PER_LANE; ++v) {
+        int4 q;
+        q.x = pack_bf16x2(acc[v * 8 + 0], acc[v * 8 + 1]);
+        q.y = pack_bf16x2(acc[v * 8 + 2], acc[v * 8 + 3]);
+        q.z = pack_bf16x2(acc[v * 8 + 4], acc[v * 8 + 5]);
+        q.w = pack_bf16x2(acc[v * 8 + 6], acc[v * 8 + 7]);
+        op[v * 32 + lane] = q;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward of combine (gate side): dw[b,j] = <g[b], y_j>;  dlogit_j = w_j (dw_j - sum_i w_i dw_i)
+// scattered into the gradient of the grid logits [B, gs.total]
+// ------------------------------------------------------------------------------------------------
+struct GateBwdArgs {
+    long long yo_off;         // symmetric expert outputs [max_rows, H]
+    const bf16* grad;         // [B, H] grad w.r.t. the layer output
+    const int* idx;
+    const int* pair_row;
+    const float* w;
+    float* dlogits;           // [B, gs.total]
+    int B, k, H, E_loc;
+};
+
+template <int VEC_PER_LANE>
+__global__ void __launch_bounds__(256) gate_bwd_kernel(Peers peers, GateBwdArgs a, GridSpec gs) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * 8 + warp;
+    if (b >= a.B) return;
+    float g[VEC_PER_LANE * 8];
+    const int4* gp = reinterpret_cast<const int4*>(a.grad + static_cast<long long>(b) * a.H);
+#pragma unroll
+    for (int v = 0; v < VEC_PER_LANE; ++v) {
+        const int4 q = ld_nc_v4(gp + v * 32 + lane);
+        const uint32_t u[4] = {(uint32_t)q.x, (uint32_t)q.y, (uint32_t)q.z, (uint32_t)q.w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const float2 f = unpack_bf16x2(u[t]);
+            g[v * 8 + 2 * t] = f.x;
+            g[v * 8 + 2 * t + 1] = f.y;
+        }
+    }
+    float dw[MAX_K], wj[MAX_K];
+    int ej[MAX_K];
+    float dot_sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < MAX_K; ++j) {
+        dw[j] = 0.f;
+        wj[j] = 0.f;
+        ej[j] = -1;
+        if (j < a.k) {
+            const long long p = static_cast<long long>(b) * a.k + j;
+            const int e = a.idx[p];
+            const int row = a.pair_row[p];
+            if (e >= 0 && row >= 0) {
+                const int4* sp = reinterpret_cast<const int4*>(peers.base[e / a.E_loc] + a.yo_off) +
+                                 static_cast<long long>(row) * (a.H / 8);
+                float d = 0.f;
+#pragma unroll
+                for (int v = 0; v < VEC_PER_LANE; ++v) {
+                    const int4 q = ld_v4(sp + v * 32 + lane);
+                    const uint32_t u[4] = {(uint32_t)q.x, (uint32_t)q.y, (uint32_t)q.z, (uint32_t)q.w};
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const float2 f = unpack_bf16x2(u[t]);
+                        d += g[v * 8 + 2 * t] * f.x + g[v * 8 + 2 * t + 1] * f.y;
+                    }
+                }
+                d = warp_sum(d);
+                dw[j] = d;
+                wj[j] = a.w[p];
+                ej[j] = e;
+                dot_sum += wj[j] * d;
+            }
+        }
+    }
+    float* dl = a.dlogits + static_cast<long long>(b) * gs.total;
+    for (int i = lane; i < gs.total; i += 32) dl[i] = 0.f;
+    __syncwarp();
+    if (lane == 0) {
+#pragma unroll
+        for (int j = 0; j < MAX_K; ++j) {
+            if (ej[j] < 0) continue;
+            const float d = wj[j] * (dw[j] - dot_sum);
+            int rem = ej[j];
+            for (int dd = gs.ndim - 1; dd >= 0; --dd) {
+                const int i = rem % gs.size[dd];
+                rem /= gs.size[dd];
+                dl[gs.offset[dd] + i] += d;
+            }
+        }
+    }
+}
+
+static Peers g_peers = {};
+static bool g_peers_set = false;
+
+}  // namespace lah
+
+using namespace lah;
+
+extern "C" {
+
+// ---- peer table (set once after the symmetric heap rendezvous; see symm.cu / parallel/symmetric.py)
+int lah_set_peers(const unsigned long long* bases, int world, int me) {
+    if (world < 1 || world > MAX_WORLD || me < 0 || me >= world) return -2;
+    for (int i = 0; i < MAX_WORLD; ++i) g_peers.base[i] = i < world ? reinterpret_cast<char*>(bases[i]) : nullptr;
+    g_peers.world = world;
+    g_peers.me = me;
+    g_peers_set = true;
+    return 0;
+}
+
+static int make_grid_spec(GridSpec* gs, const int* grid, int ndim) {
+    if (ndim < 1 || ndim > MAX_GRID_DIMS) return -2;
+    gs->ndim = ndim;
+    gs->total = 0;
+    gs->num_experts = 1;
+    for (int d = 0; d < MAX_GRID_DIMS; ++d) {
+        gs->size[d] = d < ndim ? grid[d] : 1;
+        gs->offset[d] = gs->total;
+        if (d < ndim) {
+            gs->total += grid[d];
+            gs->num_experts *= grid[d];
+        }
+    }
+    return 0;
+}
+
+int lah_gate_topk(const float* logits, int B, const int* grid, int ndim, int k, const unsigned char* alive,
+                  float failure_rate, unsigned long long seed, long long token_offset, int* idx, float* w, int* pos,
+                  int* counts, cudaStream_t st) {
+    GridSpec gs;
+    if (make_grid_spec(&gs, grid, ndim)) return -2;
+    if (k < 1 || k > MAX_K) return -3;
+    if (B <= 0) return 0;
+    gate_topk_kernel<<<(B + 7) / 8, 256, 8 * gs.total * sizeof(float), st>>>(logits, B, gs, k, alive, failure_rate, seed,
+                                                                           token_offset, idx, w, pos, counts);
+    return -(int)cudaGetLastError();
+}
+
+int lah_layout_exchange(long long cnt_all_off, long long flags_off, int slot, int epoch, int E, int E_loc, int max_rows,
+                        int* counts, int* dst_row, int* group_off, int* group_rows, int* tile_group, int* total_rows,
+                        int* status, cudaStream_t st) {
+    if (!g_peers_set) return -10;
+    LayoutArgs a;
+    a.cnt_all_off = cnt_all_off; a.flags_off = flags_off; a.slot = slot; a.epoch = epoch; a.E = E; a.E_loc = E_loc;
+    a.max_rows = max_rows; a.max_tiles = max_rows / 128; a.counts = counts; a.dst_row = dst_row; a.group_off = group_off;
+    a.group_rows = group_rows; a.tile_group = tile_group; a.total_rows = total_rows; a.status = status;
+    layout_exchange_kernel<<<1, 1024, 0, st>>>(g_peers, a);
+    return -(int)cudaGetLastError();
+}
+
+int lah_scatter_rows(const void* src, const float* scale, const int* idx, const int* pos, const int* dst_row,
+                     int* pair_row, long long dst_off, long long flags_off, int slot, int epoch, int num_pairs, int k,
+                     int H, int E_loc, int max_rows, const int* group_off, const int* group_rows, int* done_counter,
+                     int* status, cudaStream_t st) {
+    if (!g_peers_set) return -10;
+    ScatterArgs a;
+    a.src = (const bf16*)src; a.scale = scale; a.idx = idx; a.pos = pos; a.dst_row = dst_row; a.pair_row = pair_row;
+    a.dst_off = dst_off; a.flags_off = flags_off; a.slot = slot; a.epoch = epoch; a.num_pairs = num_pairs; a.k = k;
+    a.H = H; a.E_loc = E_loc; a.max_rows = max_rows; a.group_off = group_off; a.group_rows = group_rows;
+    a.pair_blocks = (num_pairs + 7) / 8; a.done_counter = done_counter; a.status = status;
+    const int pad_blocks = E_loc < 64 ? E_loc : 64;
+    const int grid = a.pair_blocks + pad_blocks;
+    if (H == 256) scatter_rows_kernel<1><<<grid, 256, 0, st>>>(g_peers, a);
+    else if (H == 512) scatter_rows_kernel<2><<<grid, 256, 0, st>>>(g_peers, a);
+    else if (H == 1024) scatter_rows_kernel<4><<<grid, 256, 0, st>>>(g_peers, a);
+    else return -2;
+    return -(int)cudaGetLastError();
+}
+
+int lah_signal_wait(long long flags_off, int slot, int epoch, int do_signal, int do_wait, int* status,
+                    cudaStream_t st) {
+    if (!g_peers_set) return -10;
+    signal_wait_kernel<<<1, 32, 0, st>>>(g_peers, flags_off, slot, epoch, do_signal, do_wait, status);
+    return -(int)cudaGetLastError();
+}
+
+int lah_combine_rows(long long src_off, const int* idx, const int* pair_row, const float* w, void* out, int B, int k,
+                     int H, int E_loc, cudaStream_t st) {
+    if (!g_peers_set) return -10;
+    if (B <= 0) return 0;
+    CombineArgs a;
+    a.src_off = src_off; a.idx = idx; a.pair_row = pair_row; a.w = w; a.out = (bf16*)out; a.B = B; a.k = k; a.H = H;
+    a.E_loc = E_loc;
+    const int grid = (B + 7) / 8;
+    if (H == 256) combine_rows_kernel<1><<<grid, 256, 0, st>>>(g_peers, a);
+    else if (H == 512) combine_rows_kernel<2><<<grid, 256, 0, st>>>(g_peers, a);
+    else if (H == 1024) combine_rows_kernel<4><<<grid, 256, 0, st>>>(g_peers, a);
+    else return -2;
+    return -(int)cudaGetLastError();
+}
+
+int lah_gate_bwd(long long yo_off, const void* grad, const int* idx, const int* pair_row, const float* w,
+                 float* dlogits, int B, int k, int H, int E_loc, const int* grid_sizes, int ndim, cudaStream_t st) {
+    if (!g_peers_set) return -10;
+    if (B <= 0) return 0;
+    GridSpec gs;
+    if (make_grid_spec(&gs, grid_sizes, ndim)) return -2;
+    if (k > MAX_K) return -3;
+    GateBwdArgs a;
+    a.yo_off = yo_off; a.grad = (const bf16*)grad; a.idx = idx; a.pair_row = pair_row; a.w = w; a.dlogits = dlogits;
+    a.B = B; a.k = k; a.H = H; a.E_loc = E_loc;
+    const int grid = (B + 7) / 8;
+    if (H == 256) gate_bwd_kernel<1><<<grid, 256, 0, st>>>(g_peers, a, gs);
+    else if (H == 512) gate_bwd_kernel<2><<<grid, 256, 0, st>>>(g_peers, a, gs);
+    else if (H == 1024) gate_bwd_kernel<4><<<grid, 256, 0, st>>>(g_peers, a, gs);
+    else return -2;
+    return -(int)cudaGetLastError();
+}
+
+}  // extern "C"

@@ -1,0 +1,219 @@
+"""
+Python entry points for the non-GEMM sm_100a kernels (csrc/layernorm.cu, csrc/moe.cu, csrc/adam.cu) and their PyTorch
+oracles.  All wrappers launch on the current CUDA stream, never synchronise, and are CUDA-graph capturable.
+"""
+import ctypes
+
+import torch
+import torch.nn.functional as F
+
+from . import native
+from .native import c_void_p, c_int, c_ll, c_float, ptr, stream_ptr
+
+c_ull = ctypes.c_ulonglong
+_configured = False
+
+SLOT_COUNTS, SLOT_DISPATCH, SLOT_OUTPUT, SLOT_GRAD, SLOT_DINPUT, SLOT_TRAINER, SLOT_BARRIER = range(7)
+NUM_SLOTS = 8
+MAX_WORLD = 8
+STATUS_TIMEOUT, STATUS_OVERFLOW = 1, 2
+
+
+def _lib():
+    global _configured
+    lib = native.cuda_lib()
+    if _configured:
+        return lib
+    P, I, L, Fl = c_void_p, c_int, c_ll, c_float
+    sigs = {
+        "lah_ln_relu_fwd": [P, P, P, P, P, P, P, I, I, I, P],
+        "lah_ln_relu_bwd": [P, P, P, P, P, P, P, P, P, P, P, I, I, I, P],
+        "lah_grouped_colsum": [P, L, P, I, P, I, P],
+        "lah_set_peers": [P, I, I],
+        "lah_gate_topk": [P, I, P, I, I, P, Fl, c_ull, L, P, P, P, P, P],
+        "lah_layout_exchange": [L, L, I, I, I, I, I, P, P, P, P, P, P, P, P],
+        "lah_scatter_rows": [P, P, P, P, P, P, L, L, I, I, I, I, I, I, I, P, P, P, P, P],
+        "lah_signal_wait": [L, I, I, I, I, P, P],
+        "lah_combine_rows": [L, P, P, P, P, I, I, I, I, P],
+        "lah_gate_bwd": [L, P, P, P, P, P, I, I, I, I, P, I, P],
+        "lah_adam_step": [P, P, P, P, P, P, I, P, I, P, P, I, Fl, Fl, Fl, Fl, Fl, I, I, I, L, P, Fl, P],
+        "lah_bump_steps": [P, P, I, P],
+        "lah_cast_bf16": [P, P, L, P],
+        "lah_symm_alloc": [c_ull, ctypes.POINTER(c_void_p)],
+        "lah_symm_free": [P],
+        "lah_symm_get_handle": [P, ctypes.c_char_p],
+        "lah_symm_open_handle": [ctypes.c_char_p, ctypes.POINTER(c_void_p)],
+        "lah_symm_close_handle": [P],
+        "lah_device_sync": [],
+    }
+    for name, argtypes in sigs.items():
+        fn = getattr(lib, name)
+        fn.restype = c_int
+        fn.argtypes = argtypes
+    _configured = True
+    return lib
+
+
+def _grid_array(grid_size):
+    return (c_int * len(grid_size))(*[int(g) for g in grid_size])
+
+
+# ---------------------------------------------------------------------------------------------------------
+# LayerNorm + ReLU over expert-grouped rows
+# ---------------------------------------------------------------------------------------------------------
+def ln_relu_fwd(h, gamma, beta, tile_group, *, out, mean, rstd, relu=True):
+    rows, C = h.shape
+    assert h.is_contiguous() and out.is_contiguous() and gamma.dtype == torch.float32
+    native.check(_lib().lah_ln_relu_fwd(ptr(h), ptr(out), ptr(mean), ptr(rstd), ptr(gamma), ptr(beta), ptr(tile_group),
+                                        rows, C, int(relu), stream_ptr()), "lah_ln_relu_fwd")
+    native.count_launch()
+    return out
+
+
+def ln_relu_bwd(da, h, mean, rstd, gamma, beta, tile_group, *, dh, dgamma, dbeta, dbias, relu=True):
+    rows, C = h.shape
+    assert da.is_contiguous() and h.is_contiguous() and dh.is_contiguous()
+    native.check(_lib().lah_ln_relu_bwd(ptr(da), ptr(h), ptr(mean), ptr(rstd), ptr(gamma), ptr(beta), ptr(dh),
+                                        ptr(dgamma), ptr(dbeta), ptr(dbias), ptr(tile_group), rows, C, int(relu),
+                                        stream_ptr()), "lah_ln_relu_bwd")
+    native.count_launch()
+    return dh
+
+
+def grouped_colsum(x, tile_group, *, out):
+    rows, C = x.shape
+    native.check(_lib().lah_grouped_colsum(ptr(x), x.stride(0), ptr(out), C, ptr(tile_group), rows, stream_ptr()),
+                 "lah_grouped_colsum")
+    native.count_launch()
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# routing / P2P all-to-all
+# ---------------------------------------------------------------------------------------------------------
+def set_peers(bases, me):
+    arr = (c_ull * len(bases))(*[int(b) for b in bases])
+    native.check(_lib().lah_set_peers(ctypes.cast(arr, c_void_p), len(bases), me), "lah_set_peers")
+
+
+def gate_topk(logits, grid_size, k, *, alive=None, failure_rate=0.0, seed=0, token_offset=0, idx, w, pos, counts):
+    B = logits.shape[0]
+    assert logits.dtype == torch.float32 and logits.is_contiguous() and logits.shape[1] == sum(grid_size)
+    native.check(_lib().lah_gate_topk(ptr(logits), B, ctypes.cast(_grid_array(grid_size), c_void_p), len(grid_size), k,
+                                      ptr(alive), float(failure_rate), int(seed) & (2 ** 64 - 1), int(token_offset),
+                                      ptr(idx), ptr(w), ptr(pos), ptr(counts), stream_ptr()), "lah_gate_topk")
+    native.count_launch()
+
+
+def layout_exchange(cnt_all_off, flags_off, slot, epoch, E, E_loc, max_rows, *, counts, dst_row, group_off, group_rows,
+                    tile_group, total_rows, status):
+    native.check(_lib().lah_layout_exchange(cnt_all_off, flags_off, slot, epoch, E, E_loc, max_rows, ptr(counts),
+                                            ptr(dst_row), ptr(group_off), ptr(group_rows), ptr(tile_group),
+                                            ptr(total_rows), ptr(status), stream_ptr()), "lah_layout_exchange")
+    native.count_launch()
+
+
+def scatter_rows(src, scale, idx, pos, dst_row, pair_row, dst_off, flags_off, slot, epoch, k, E_loc, max_rows,
+                 group_off, group_rows, done_counter, status):
+    num_pairs = idx.numel()
+    H = src.shape[1]
+    assert src.is_contiguous() and src.dtype == torch.bfloat16
+    native.check(_lib().lah_scatter_rows(ptr(src), ptr(scale), ptr(idx), ptr(pos), ptr(dst_row), ptr(pair_row), dst_off,
+                                         flags_off, slot, epoch, num_pairs, k, H, E_loc, max_rows, ptr(group_off),
+                                         ptr(group_rows), ptr(done_counter), ptr(status), stream_ptr()),
+                 "lah_scatter_rows")
+    native.count_launch()
+
+
+def signal_wait(flags_off, slot, epoch, status, *, signal=True, wait=True):
+    native.check(_lib().lah_signal_wait(flags_off, slot, epoch, int(signal), int(wait), ptr(status), stream_ptr()),
+                 "lah_signal_wait")
+    native.count_launch()
+
+
+def combine_rows(src_off, idx, pair_row, w, out, k, E_loc):
+    B, H = out.shape
+    native.check(_lib().lah_combine_rows(src_off, ptr(idx), ptr(pair_row), ptr(w), ptr(out), B, k, H, E_loc,
+                                         stream_ptr()), "lah_combine_rows")
+    native.count_launch()
+    return out
+
+
+def gate_bwd(yo_off, grad, idx, pair_row, w, dlogits, k, E_loc, grid_size):
+    B, H = grad.shape
+    assert grad.is_contiguous() and grad.dtype == torch.bfloat16 and dlogits.dtype == torch.float32
+    native.check(_lib().lah_gate_bwd(yo_off, ptr(grad), ptr(idx), ptr(pair_row), ptr(w), ptr(dlogits), B, k, H, E_loc,
+                                     ctypes.cast(_grid_array(grid_size), c_void_p), len(grid_size), stream_ptr()),
+                 "lah_gate_bwd")
+    native.count_launch()
+    return dlogits
+
+
+# ---------------------------------------------------------------------------------------------------------
+# optimizer
+# ---------------------------------------------------------------------------------------------------------
+def adam_step(p, g, m, v, vmax, p_bf16, seg_sizes, G, *, step=None, group_rows=None, step_scalar=0, lr=1e-3,
+              betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, amsgrad=True, zero_mask=0, world=1,
+              peer_grad_off=-1, peer_bases=None, grad_scale=1.0):
+    arr = None
+    if peer_bases is not None:
+        arr = (c_ull * len(peer_bases))(*[int(b) for b in peer_bases])
+    """
+    One fused Adam/AMSGrad step over a flat fp32 buffer laid out as consecutive segments [G, seg_sizes[s]].
+    :param step: int32 [G] per-group step counts (already incremented) or None -> step_scalar for everything
+    :param group_rows: int32 [G]; groups with 0 rows are skipped (experts that received no tokens are not stepped)
+    """
+    if isinstance(seg_sizes, int):
+        seg_sizes = [seg_sizes]
+    segs = (c_ll * len(seg_sizes))(*[int(s) for s in seg_sizes])
+    native.check(_lib().lah_adam_step(ptr(p), ptr(g), ptr(m), ptr(v), ptr(vmax), ptr(p_bf16), len(seg_sizes),
+                                      ctypes.cast(segs, c_void_p), G, ptr(step),
+                                      ptr(group_rows), int(step_scalar), lr, betas[0], betas[1], eps, weight_decay,
+                                      int(amsgrad), int(zero_mask), world, peer_grad_off,
+                                      ctypes.cast(arr, c_void_p) if arr is not None else c_void_p(0), grad_scale,
+                                      stream_ptr()), "lah_adam_step")
+    native.count_launch()
+
+
+def bump_steps(step, group_rows):
+    native.check(_lib().lah_bump_steps(ptr(step), ptr(group_rows), step.numel(), stream_ptr()), "lah_bump_steps")
+    native.count_launch()
+
+
+def cast_bf16(src, dst):
+    assert src.dtype == torch.float32 and dst.dtype == torch.bfloat16 and src.numel() == dst.numel()
+    native.check(_lib().lah_cast_bf16(ptr(src), ptr(dst), src.numel(), stream_ptr()), "lah_cast_bf16")
+    native.count_launch()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# PyTorch oracles
+# ---------------------------------------------------------------------------------------------------------
+def product_key_scores(logits, grid_size):
+    """[B, sum(grid)] grid logits -> [B, prod(grid)] expert scores (expert id = row-major index over the grid)."""
+    parts = torch.split(logits, list(grid_size), dim=-1)
+    scores = parts[0]
+    for part in parts[1:]:
+        scores = (scores.unsqueeze(-1) + part.unsqueeze(-2)).flatten(-2)
+    return scores
+
+
+def gate_topk_ref(logits, grid_size, k, alive=None, fail_mask=None):
+    """returns idx [B,k] (-1 for missing), weights [B,k] (softmax over alive selected)"""
+    scores = product_key_scores(logits.float(), grid_size)
+    dead = torch.zeros_like(scores, dtype=torch.bool)
+    if alive is not None:
+        dead |= ~alive.bool().view(1, -1)
+    if fail_mask is not None:
+        dead |= fail_mask
+    scores = scores.masked_fill(dead, float("-inf"))
+    top_v, top_i = torch.topk(scores, k, dim=-1)
+    valid = torch.isfinite(top_v)
+    w = torch.softmax(top_v.masked_fill(~valid, float("-inf")), dim=-1)
+    w = torch.where(valid, w, torch.zeros_like(w)).nan_to_num(0.0)
+    return torch.where(valid, top_i, torch.full_like(top_i, -1)), w
+
+
+def ln_relu_ref(h, gamma, beta, relu=True):
+    y = F.layer_norm(h.float(), (h.shape[-1],), gamma.float(), beta.float(), 1e-5)
+    return F.relu(y) if relu else y

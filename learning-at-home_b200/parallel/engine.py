@@ -1,0 +1,446 @@
+"""
+The in-box DMoE engine: every rank (one process per B200) is BOTH a trainer and the host of a shard of experts.
+
+Mapping to the reference:
+  * ``GatingFunction.forward``  (/root/reference/lib/client/gating_function.py:25-66)   -> ``FusedDMoE.forward``
+  * ``RemoteExpert`` fwd/bwd RPCs (/root/reference/lib/client/remote_expert.py:53-76)   -> P2P scatter / combine kernels
+  * ``TaskPool`` batching (/root/reference/lib/runtime/task_pool.py:105-172)            -> expert-grouped row layout
+  * ``ExpertBackend.forward/backward/apply_gradients`` (lib/runtime/expert_backend.py:64-97)
+                                                            -> grouped tcgen05 GEMMs, fused LN/ReLU, fused Adam(AMSGrad)
+  * DHT liveness (/root/reference/lib/network/__init__.py:88-129)                       -> ``alive`` table read by the gate
+
+Activations of the experts stay resident on the expert's GPU between forward and backward (the reference recomputes
+the forward and re-sends the inputs); the optimizer step of an expert happens inside the backward pass, once per step,
+for experts that received at least one row — per-expert Adam state and step counters, exactly like one
+``torch.optim.Adam(amsgrad=True)`` per ``ExpertBackend``.
+
+On a machine without a GPU the same modules run a plain PyTorch implementation of identical maths (``_forward_ref``),
+which is also the numerical oracle of the GPU tests.
+"""
+import math
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from ..ops import gemm, kernels as K, native
+
+SEG_NAMES = ("w1", "b1", "g1", "be1", "w2", "b2", "g2", "be2", "w3", "b3")
+#: name of each segment inside a reference FeedforwardBlock state_dict (layers.py:8-16)
+REF_KEYS = {"w1": "layers.0.weight", "b1": "layers.0.bias", "g1": "layers.1.weight", "be1": "layers.1.bias",
+            "w2": "layers.3.weight", "b2": "layers.3.bias", "g2": "layers.4.weight", "be2": "layers.4.bias",
+            "w3": "layers.6.weight", "b3": "layers.6.bias"}
+SMALL_SEG_MASK = sum(1 << i for i, n in enumerate(SEG_NAMES) if not n.startswith("w"))
+
+
+@dataclass
+class DMoEConfig:
+    hidden: int = 512
+    grid_size: Tuple[int, ...] = (8, 8)
+    k: int = 4
+    num_layers: int = 4
+    in_features: int = 784
+    num_classes: int = 10
+    tokens_per_rank: int = 1024          # maximum batch (rows) a rank feeds per step
+    capacity_factor: float = 2.0         # receive-buffer rows = capacity_factor * tokens_per_rank * k (+ padding)
+    failure_rate: float = 0.0            # Bernoulli per (token, expert) failure injection (faulty_dmoe_emulator.py:49-51)
+    lr: float = 1e-3
+    betas: Tuple[float, float] = (0.9, 0.999)
+    eps: float = 1e-8
+    amsgrad: bool = True
+    seed: int = 1337
+    uid_prefix: str = "expert"
+
+    @property
+    def num_experts(self) -> int:
+        return int(math.prod(self.grid_size))
+
+    @property
+    def inner(self) -> int:
+        return 4 * self.hidden
+
+    def seg_shapes(self) -> Dict[str, Tuple[int, ...]]:
+        H, I = self.hidden, self.inner
+        return {"w1": (I, H), "b1": (I,), "g1": (I,), "be1": (I,), "w2": (I, I), "b2": (I,), "g2": (I,), "be2": (I,),
+                "w3": (H, I), "b3": (H,)}
+
+
+def expert_uid(cfg: DMoEConfig, e: int) -> str:
+    """global expert index -> 'prefix.i0.i1...' (row-major over the grid; reference uid schema README.md:106)"""
+    parts = []
+    for size in reversed(cfg.grid_size):
+        parts.append(str(e % size))
+        e //= size
+    return ".".join([cfg.uid_prefix] + parts[::-1])
+
+
+# =========================================================================================================
+# process-wide context: symmetric heap, flags, epochs
+# =========================================================================================================
+class EngineContext:
+    """Per-process state shared by all DMoE layers: symmetric heap, signal flags, scratch counters, epoch counter."""
+
+    def __init__(self, cfg: DMoEConfig, group=None, device=None, heap_bytes: Optional[int] = None):
+        from .symmetric import SymmetricHeap
+        import torch.distributed as dist
+        self.cfg = cfg
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        distributed = dist.is_available() and dist.is_initialized()
+        self.world = dist.get_world_size(group) if distributed else 1
+        self.rank = dist.get_rank(group) if distributed else 0
+        assert cfg.num_experts % self.world == 0, "experts must divide evenly over ranks"
+        self.E = cfg.num_experts
+        self.E_loc = self.E // self.world
+        pairs = cfg.tokens_per_rank * cfg.k
+        cap = pairs if self.world == 1 else int(math.ceil(pairs * cfg.capacity_factor))
+        self.max_rows = ((cap + 127) // 128 + self.E_loc) * 128
+        self.max_tiles = self.max_rows // 128
+        H = cfg.hidden
+        sym_rows_bytes = self.max_rows * H * 2
+        need = (2 * cfg.num_layers + 2) * (sym_rows_bytes + 4096) + K.MAX_WORLD * self.E * 4 + (1 << 20)
+        self.heap = SymmetricHeap(heap_bytes or need, group=group, device=self.device)
+        self.flags, self.flags_off = self.heap.alloc((K.NUM_SLOTS, K.MAX_WORLD), torch.int32)
+        self.cnt_all, self.cnt_all_off = self.heap.alloc((K.MAX_WORLD, self.E), torch.int32)
+        i32 = dict(dtype=torch.int32, device=self.device)
+        self.counts = torch.zeros(self.E, **i32)
+        self.done_counter = torch.zeros(1, **i32)
+        self.status = torch.zeros(1, **i32)
+        self.alive = torch.ones(self.E, dtype=torch.uint8, device=self.device)
+        self.epoch = 0
+        self.token_counter = 0
+        # transient backward buffers shared by all layers
+        self.gyd, self.gyd_off = self.heap.alloc((self.max_rows, H), torch.bfloat16)
+        self.dxd, self.dxd_off = self.heap.alloc((self.max_rows, H), torch.bfloat16)
+        bf = dict(dtype=torch.bfloat16, device=self.device)
+        self.da = torch.empty(self.max_rows, cfg.inner, **bf)
+        self.dh = torch.empty(self.max_rows, cfg.inner, **bf)
+        self.heap.barrier()
+
+    def next_epoch(self) -> int:
+        self.epoch += 1
+        return self.epoch
+
+    def check_status(self):
+        """host-side check of the device status word (synchronises); raises on timeouts / capacity overflow"""
+        code = int(self.status.item())
+        if code & K.STATUS_TIMEOUT:
+            raise RuntimeError("DMoE engine: timed out waiting for a peer GPU (dead rank?)")
+        if code & K.STATUS_OVERFLOW:
+            raise RuntimeError("DMoE engine: expert receive buffer overflow; raise DMoEConfig.capacity_factor")
+
+
+# =========================================================================================================
+# expert parameters of one DMoE layer hosted on this rank
+# =========================================================================================================
+class ExpertShard:
+    """Stacked parameters / gradients / Adam state of the E_loc local experts of one layer (flat fp32 buffers, segments
+    [E_loc, size] per tensor kind) plus the bf16 mirror consumed by the GEMMs."""
+
+    def __init__(self, cfg: DMoEConfig, E_loc: int, first_expert: int, device, layer_index: int = 0):
+        self.cfg, self.E_loc, self.first_expert = cfg, E_loc, first_expert
+        shapes = cfg.seg_shapes()
+        self.seg_sizes = [int(math.prod(shapes[n])) for n in SEG_NAMES]
+        total = sum(self.seg_sizes) * E_loc
+        f32 = dict(dtype=torch.float32, device=device)
+        self.p = torch.empty(total, **f32)
+        self.g = torch.zeros(total, **f32)
+        self.m = torch.zeros(total, **f32)
+        self.v = torch.zeros(total, **f32)
+        self.vmax = torch.zeros(total, **f32) if cfg.amsgrad else None
+        self.p_bf16 = torch.empty(total, dtype=torch.bfloat16, device=device)
+        self.step = torch.zeros(E_loc, dtype=torch.int32, device=device)
+        self.views: Dict[str, torch.Tensor] = {}
+        self.grads: Dict[str, torch.Tensor] = {}
+        self.bf16: Dict[str, torch.Tensor] = {}
+        off = 0
+        for name, size in zip(SEG_NAMES, self.seg_sizes):
+            sl = slice(off, off + size * E_loc)
+            self.views[name] = self.p[sl].view(E_loc, *shapes[name])
+            self.grads[name] = self.g[sl].view(E_loc, *shapes[name])
+            self.bf16[name] = self.p_bf16[sl].view(E_loc, *shapes[name])
+            off += size * E_loc
+        self.reset_parameters(layer_index)
+
+    @torch.no_grad()
+    def reset_parameters(self, layer_index: int = 0):
+        """nn.Linear / nn.LayerNorm default initialisation, seeded per (layer, global expert) so that the same expert
+        gets the same weights regardless of the number of ranks"""
+        cfg = self.cfg
+        for le in range(self.E_loc):
+            gen = torch.Generator(device="cpu")
+            gen.manual_seed(cfg.seed * 1000003 + layer_index * 10007 + self.first_expert + le)
+            for w, b in (("w1", "b1"), ("w2", "b2"), ("w3", "b3")):
+                fan_in = self.views[w].shape[-1]
+                bound = 1.0 / math.sqrt(fan_in)
+                self.views[w][le].copy_((torch.rand(self.views[w][le].shape, generator=gen) * 2 - 1) * bound)
+                self.views[b][le].copy_((torch.rand(self.views[b][le].shape, generator=gen) * 2 - 1) * bound)
+            for gname, bname in (("g1", "be1"), ("g2", "be2")):
+                self.views[gname][le].fill_(1.0)
+                self.views[bname][le].zero_()
+        self.sync_bf16()
+
+    def sync_bf16(self):
+        if self.p.is_cuda:
+            K.cast_bf16(self.p, self.p_bf16)
+        else:
+            self.p_bf16.copy_(self.p)
+
+    # ------------------------------------------------------------------ checkpoint layout
+    def expert_state_dict(self, le: int, prefix: str = "expert.") -> Dict[str, torch.Tensor]:
+        """state of local expert `le` with the key names of ``ExpertBackend.state_dict()`` of the reference"""
+        return {prefix + REF_KEYS[n]: self.views[n][le].detach().clone().cpu() for n in SEG_NAMES}
+
+    def expert_optimizer_state(self, le: int) -> Dict:
+        """torch.optim.Adam-compatible state_dict of local expert `le` (parameter order = module.parameters())"""
+        state = {}
+        for i, n in enumerate(SEG_NAMES):
+            off = self._seg_offset(n) + le * self.seg_sizes[i]
+            sl = slice(off, off + self.seg_sizes[i])
+            shape = self.views[n].shape[1:]
+            entry = dict(step=torch.tensor(float(self.step[le].item())), exp_avg=self.m[sl].view(shape).clone().cpu(),
+                         exp_avg_sq=self.v[sl].view(shape).clone().cpu())
+            if self.vmax is not None:
+                entry["max_exp_avg_sq"] = self.vmax[sl].view(shape).clone().cpu()
+            state[i] = entry
+        cfg = self.cfg
+        group = dict(lr=cfg.lr, betas=cfg.betas, eps=cfg.eps, weight_decay=0, amsgrad=cfg.amsgrad,
+                     params=list(range(len(SEG_NAMES))))
+        return dict(state=state, param_groups=[group])
+
+    def load_expert_state_dict(self, le: int, state: Dict[str, torch.Tensor], prefix: str = "expert."):
+        with torch.no_grad():
+            for n in SEG_NAMES:
+                self.views[n][le].copy_(state[prefix + REF_KEYS[n]])
+        self.sync_bf16()
+
+    def load_expert_optimizer_state(self, le: int, opt_state: Dict):
+        with torch.no_grad():
+            for i, n in enumerate(SEG_NAMES):
+                entry = opt_state["state"].get(i)
+                if entry is None:
+                    continue
+                off = self._seg_offset(n) + le * self.seg_sizes[i]
+                sl = slice(off, off + self.seg_sizes[i])
+                self.m[sl].copy_(entry["exp_avg"].reshape(-1))
+                self.v[sl].copy_(entry["exp_avg_sq"].reshape(-1))
+                if self.vmax is not None and "max_exp_avg_sq" in entry:
+                    self.vmax[sl].copy_(entry["max_exp_avg_sq"].reshape(-1))
+                self.step[le] = int(entry["step"])
+
+    def _seg_offset(self, name: str) -> int:
+        off = 0
+        for n, size in zip(SEG_NAMES, self.seg_sizes):
+            if n == name:
+                return off
+            off += size * self.E_loc
+        raise KeyError(name)
+
+
+# =========================================================================================================
+# per-layer workspace (activations that stay resident between forward and backward)
+# =========================================================================================================
+class LayerWorkspace:
+    def __init__(self, ctx: EngineContext):
+        cfg, dev, R = ctx.cfg, ctx.device, ctx.max_rows
+        H, I = cfg.hidden, cfg.inner
+        bf = dict(dtype=torch.bfloat16, device=dev)
+        i32 = dict(dtype=torch.int32, device=dev)
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.xd, self.xd_off = ctx.heap.alloc((R, H), torch.bfloat16)   # dispatched inputs (peers push)
+        self.yo, self.yo_off = ctx.heap.alloc((R, H), torch.bfloat16)   # expert outputs (peers pull)
+        self.h1, self.a1 = torch.empty(R, I, **bf), torch.empty(R, I, **bf)
+        self.h2, self.a2 = torch.empty(R, I, **bf), torch.empty(R, I, **bf)
+        self.mean1, self.rstd1 = torch.empty(R, **f32), torch.empty(R, **f32)
+        self.mean2, self.rstd2 = torch.empty(R, **f32), torch.empty(R, **f32)
+        P = cfg.tokens_per_rank * cfg.k
+        self.idx, self.pos, self.pair_row = torch.empty(P, **i32), torch.empty(P, **i32), torch.empty(P, **i32)
+        self.w = torch.empty(P, **f32)
+        self.dst_row = torch.empty(ctx.E, **i32)
+        self.group_off = torch.zeros(ctx.E_loc + 1, **i32)
+        self.group_rows = torch.zeros(ctx.E_loc, **i32)
+        self.tile_group = torch.full((ctx.max_tiles,), -1, **i32)
+        self.total_rows = torch.zeros(1, **i32)
+
+
+# =========================================================================================================
+# the DMoE layer
+# =========================================================================================================
+class _FusedDMoEFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, logits, layer):
+        ctx.layer = layer
+        ctx.B = x.shape[0]
+        return layer._forward_cuda(x, logits)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        dx, dlogits = ctx.layer._backward_cuda(grad_out.contiguous(), ctx.B)
+        return dx, dlogits, None
+
+
+class FusedDMoE(nn.Module):
+    """
+    Decentralized-MoE layer over the experts of the whole box.  Trainer-side parameters: ``proj`` (product-key gating,
+    identical to ``GatingFunction.proj``: Linear(in_features, sum(grid_size))).  Expert parameters live in
+    ``self.shard`` and are updated by the layer itself during backward (they are NOT nn.Parameters, mirroring
+    ``get_non_expert_params`` of the reference emulator).
+    """
+
+    def __init__(self, cfg: DMoEConfig, ctx: Optional[EngineContext] = None, layer_index: int = 0, device=None):
+        super().__init__()
+        self.cfg, self.ctx, self.layer_index = cfg, ctx, layer_index
+        self.grid_size = tuple(cfg.grid_size)
+        self.proj = nn.Linear(cfg.hidden, sum(cfg.grid_size))
+        if ctx is not None:
+            self.E_loc, self.first_expert, dev = ctx.E_loc, ctx.rank * ctx.E_loc, ctx.device
+            self.ws = LayerWorkspace(ctx)
+        else:  # CPU / oracle mode: all experts local
+            self.E_loc, self.first_expert, dev = cfg.num_experts, 0, device or torch.device("cpu")
+            self.ws = None
+        self.shard = ExpertShard(cfg, self.E_loc, self.first_expert, dev, layer_index)
+        self.ref_fail_mask = None  # tests can inject an explicit failure mask into the oracle path
+
+    # ------------------------------------------------------------------ public forward
+    def forward(self, x):
+        assert x.dim() == 2 and x.shape[1] == self.cfg.hidden
+        logits = F.linear(x.float(), self.proj.weight, self.proj.bias)
+        if self.ctx is None:
+            return self._forward_ref(x, logits)
+        assert x.shape[0] <= self.cfg.tokens_per_rank, "batch exceeds DMoEConfig.tokens_per_rank"
+        return _FusedDMoEFunction.apply(x.to(torch.bfloat16).contiguous(), logits.contiguous(), self)
+
+    # ------------------------------------------------------------------ sm_100a path
+    def _forward_cuda(self, x, logits):
+        c, ws, sh, cfg = self.ctx, self.ws, self.shard, self.cfg
+        B, k = x.shape[0], cfg.k
+        P = B * k
+        epoch = c.next_epoch()
+        idx, w, pos, pair_row = ws.idx[:P], ws.w[:P], ws.pos[:P], ws.pair_row[:P]
+        K.gate_topk(logits, self.grid_size, k, alive=c.alive, failure_rate=cfg.failure_rate if self.training else 0.0,
+                    seed=cfg.seed * 7919 + self.layer_index, token_offset=c.token_counter, idx=idx, w=w, pos=pos,
+                    counts=c.counts)
+        c.token_counter += B
+        K.layout_exchange(c.cnt_all_off, c.flags_off, K.SLOT_COUNTS, epoch, c.E, c.E_loc, c.max_rows, counts=c.counts,
+                          dst_row=ws.dst_row, group_off=ws.group_off, group_rows=ws.group_rows,
+                          tile_group=ws.tile_group, total_rows=ws.total_rows, status=c.status)
+        K.scatter_rows(x, None, idx, pos, ws.dst_row, pair_row, ws.xd_off, c.flags_off, K.SLOT_DISPATCH, epoch, k,
+                       c.E_loc, c.max_rows, ws.group_off, ws.group_rows, c.done_counter, c.status)
+        if c.world > 1:
+            K.signal_wait(c.flags_off, K.SLOT_DISPATCH, epoch, c.status, signal=False, wait=True)
+        # ---- expert FFN on the rows this rank received (grouped by expert)
+        tg = ws.tile_group
+        gemm.grouped_linear(ws.xd, sh.bf16["w1"], tile_group=tg, bias=sh.views["b1"], out=ws.h1)
+        K.ln_relu_fwd(ws.h1, sh.views["g1"], sh.views["be1"], tg, out=ws.a1, mean=ws.mean1, rstd=ws.rstd1)
+        gemm.grouped_linear(ws.a1, sh.bf16["w2"], tile_group=tg, bias=sh.views["b2"], out=ws.h2)
+        K.ln_relu_fwd(ws.h2, sh.views["g2"], sh.views["be2"], tg, out=ws.a2, mean=ws.mean2, rstd=ws.rstd2)
+        gemm.grouped_linear(ws.a2, sh.bf16["w3"], tile_group=tg, bias=sh.views["b3"], residual=ws.xd, out=ws.yo)
+        if c.world > 1:
+            K.signal_wait(c.flags_off, K.SLOT_OUTPUT, epoch, c.status, signal=True, wait=True)
+        y = torch.empty(B, cfg.hidden, dtype=torch.bfloat16, device=x.device)
+        K.combine_rows(ws.yo_off, idx, pair_row, w, y, k, c.E_loc)
+        return y
+
+    def _backward_cuda(self, gy, B):
+        c, ws, sh, cfg = self.ctx, self.ws, self.shard, self.cfg
+        k = cfg.k
+        P = B * k
+        epoch = c.next_epoch()
+        idx, w, pos, pair_row = ws.idx[:P], ws.w[:P], ws.pos[:P], ws.pair_row[:P]
+        gy = gy.to(torch.bfloat16)
+        dlogits = torch.empty(B, sum(self.grid_size), dtype=torch.float32, device=gy.device)
+        K.gate_bwd(ws.yo_off, gy, idx, pair_row, w, dlogits, k, c.E_loc, self.grid_size)
+        K.scatter_rows(gy, w, idx, pos, None, pair_row, c.gyd_off, c.flags_off, K.SLOT_GRAD, epoch, k, c.E_loc,
+                       c.max_rows, ws.group_off, ws.group_rows, c.done_counter, c.status)
+        if c.world > 1:
+            K.signal_wait(c.flags_off, K.SLOT_GRAD, epoch, c.status, signal=False, wait=True)
+        tg, go, G = ws.tile_group, ws.group_off, c.E_loc
+        gr = sh.grads
+        K.grouped_colsum(c.gyd, tg, out=gr["b3"])
+        gemm.grouped_wgrad(c.gyd, ws.a2, go, G, out=gr["w3"])
+        gemm.grouped_linear(c.gyd, sh.bf16["w3"], tile_group=tg, w_is_kn=True, out=c.da)
+        K.ln_relu_bwd(c.da, ws.h2, ws.mean2, ws.rstd2, sh.views["g2"], sh.views["be2"], tg, dh=c.dh, dgamma=gr["g2"],
+                      dbeta=gr["be2"], dbias=gr["b2"])
+        gemm.grouped_wgrad(c.dh, ws.a1, go, G, out=gr["w2"])
+        gemm.grouped_linear(c.dh, sh.bf16["w2"], tile_group=tg, w_is_kn=True, out=c.da)
+        K.ln_relu_bwd(c.da, ws.h1, ws.mean1, ws.rstd1, sh.views["g1"], sh.views["be1"], tg, dh=c.dh, dgamma=gr["g1"],
+                      dbeta=gr["be1"], dbias=gr["b1"])
+        gemm.grouped_wgrad(c.dh, ws.xd, go, G, out=gr["w1"])
+        gemm.grouped_linear(c.dh, sh.bf16["w1"], tile_group=tg, w_is_kn=True, residual=c.gyd, out=c.dxd)
+        # ---- expert-side optimizer step (reference: ExpertBackend.apply_gradients right after backward)
+        self.apply_expert_gradients()
+        if c.world > 1:
+            K.signal_wait(c.flags_off, K.SLOT_DINPUT, epoch, c.status, signal=True, wait=True)
+        dx = torch.empty(B, cfg.hidden, dtype=torch.bfloat16, device=gy.device)
+        K.combine_rows(c.dxd_off, idx, pair_row, None, dx, k, c.E_loc)
+        return dx, dlogits
+
+    def apply_expert_gradients(self):
+        sh, cfg, ws = self.shard, self.cfg, self.ws
+        K.bump_steps(sh.step, ws.group_rows)
+        K.adam_step(sh.p, sh.g, sh.m, sh.v, sh.vmax, sh.p_bf16, sh.seg_sizes, self.E_loc, step=sh.step,
+                    group_rows=ws.group_rows, lr=cfg.lr, betas=cfg.betas, eps=cfg.eps, amsgrad=cfg.amsgrad,
+                    zero_mask=SMALL_SEG_MASK)
+
+    # ------------------------------------------------------------------ PyTorch oracle (CPU path, tests)
+    def _expert_params(self, e_local: int, dtype=torch.float32):
+        return {n: self.shard.views[n][e_local].to(dtype) for n in SEG_NAMES}
+
+    def _forward_ref(self, x, logits, emulate_bf16: bool = False):
+        """Dense reference of the layer: same routing, fp32 expert maths, differentiable w.r.t. x and logits only
+        (expert parameters are buffers).  ``emulate_bf16`` rounds activations like the GPU path does."""
+        cfg = self.cfg
+        idx, w_sel = K.gate_topk_ref(logits.detach(), self.grid_size, cfg.k,
+                                     alive=self.ctx.alive if self.ctx is not None else None,
+                                     fail_mask=self.ref_fail_mask)
+        # differentiable weights: softmax over the selected logits
+        scores = K.product_key_scores(logits, self.grid_size)
+        safe_idx = idx.clamp(min=0)
+        sel = torch.gather(scores, 1, safe_idx).masked_fill(idx < 0, float("-inf"))
+        weights = torch.softmax(sel, dim=-1)
+        weights = torch.where(idx >= 0, weights, torch.zeros_like(weights))
+        xf = x.float()
+        out = torch.zeros(x.shape[0], cfg.hidden, dtype=torch.float32, device=x.device)
+        rnd = (lambda t: t.to(torch.bfloat16).float()) if emulate_bf16 else (lambda t: t)
+        for e in idx[idx >= 0].unique().tolist():
+            le = e - self.first_expert
+            p = self._expert_params(le)
+            if emulate_bf16:
+                p = {n: (rnd(v) if n.startswith("w") else v) for n, v in p.items()}
+            tok, slot = torch.nonzero(idx == e, as_tuple=True)
+            xe = rnd(xf[tok])
+            h1 = rnd(F.linear(xe, p["w1"], p["b1"]))
+            a1 = rnd(F.relu(F.layer_norm(h1, (cfg.inner,), p["g1"], p["be1"])))
+            h2 = rnd(F.linear(a1, p["w2"], p["b2"]))
+            a2 = rnd(F.relu(F.layer_norm(h2, (cfg.inner,), p["g2"], p["be2"])))
+            ye = rnd(F.linear(a2, p["w3"], p["b3"]) + xe)
+            out = out.index_put((tok,), ye * weights[tok, slot].unsqueeze(-1), accumulate=True)
+        return out.to(x.dtype)
+
+
+# =========================================================================================================
+# flagship model + trainer  (convergence notebook model, cell 2: Linear -> 4 x DMoE -> LayerNorm -> Linear)
+# =========================================================================================================
+class DMoEClassifier(nn.Module):
+    def __init__(self, cfg: DMoEConfig, ctx: Optional[EngineContext] = None, device=None):
+        super().__init__()
+        self.cfg = cfg
+        self.stem = nn.Linear(cfg.in_features, cfg.hidden)
+        self.blocks = nn.ModuleList([FusedDMoE(cfg, ctx, layer_index=i, device=device) for i in range(cfg.num_layers)])
+        self.norm = nn.LayerNorm(cfg.hidden)
+        self.head = nn.Linear(cfg.hidden, cfg.num_classes)
+
+    def forward(self, x):
+        on_gpu = self.blocks[0].ctx is not None
+        if on_gpu:
+            h = F.linear(x.to(torch.bfloat16), self.stem.weight.to(torch.bfloat16), self.stem.bias.to(torch.bfloat16))
+        else:
+            h = self.stem(x)
+        for block in self.blocks:
+            h = block(h)
+        h = self.norm(h.float())
+        return self.head(h)
+
+    def non_expert_parameters(self):
+        return list(self.parameters())  # expert parameters are not nn.Parameters by construction
