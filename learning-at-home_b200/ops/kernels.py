@@ -217,3 +217,36 @@ def gate_topk_ref(logits, grid_size, k, alive=None, fail_mask=None):
 def ln_relu_ref(h, gamma, beta, relu=True):
     y = F.layer_norm(h.float(), (h.shape[-1],), gamma.float(), beta.float(), 1e-5)
     return F.relu(y) if relu else y
+
+
+@torch.no_grad()
+def adam_step_ref(p, g, m, v, vmax, seg_sizes, G, *, step, group_rows=None, lr=1e-3, betas=(0.9, 0.999), eps=1e-8,
+                  amsgrad=True, zero_mask=0):
+    """PyTorch implementation of csrc/adam.cu (flat segments [G, size]; per-group step; inactive groups skipped)."""
+    if isinstance(seg_sizes, int):
+        seg_sizes = [seg_sizes]
+    off = 0
+    active = torch.ones(G, dtype=torch.bool, device=p.device) if group_rows is None else (group_rows > 0)
+    stepf = step.to(torch.float32).clamp(min=1)
+    bc1 = (1 - betas[0] ** stepf).view(G, 1)
+    bc2 = (1 - betas[1] ** stepf).view(G, 1)
+    for s, size in enumerate(seg_sizes):
+        sl = slice(off, off + size * G)
+        P, Gr, M, V = p[sl].view(G, size), g[sl].view(G, size), m[sl].view(G, size), v[sl].view(G, size)
+        act = active.view(G, 1)
+        m_new = M + (1 - betas[0]) * (Gr - M)
+        v_new = V * betas[1] + (1 - betas[1]) * Gr * Gr
+        if amsgrad:
+            VM = vmax[sl].view(G, size)
+            vm_new = torch.maximum(VM, v_new)
+            denom = vm_new.sqrt() / bc2.sqrt() + eps
+            VM.copy_(torch.where(act, vm_new, VM))
+        else:
+            denom = v_new.sqrt() / bc2.sqrt() + eps
+        p_new = P - (lr / bc1) * (m_new / denom)
+        P.copy_(torch.where(act, p_new, P))
+        M.copy_(torch.where(act, m_new, M))
+        V.copy_(torch.where(act, v_new, V))
+        if (zero_mask >> s) & 1:
+            Gr.copy_(torch.where(act, torch.zeros_like(Gr), Gr))
+        off += size * G

@@ -99,7 +99,7 @@ class EngineContext:
         self.max_tiles = self.max_rows // 128
         H = cfg.hidden
         sym_rows_bytes = self.max_rows * H * 2
-        need = (2 * cfg.num_layers + 2) * (sym_rows_bytes + 4096) + K.MAX_WORLD * self.E * 4 + (1 << 20)
+        need = (2 * cfg.num_layers + 2) * (sym_rows_bytes + 4096) + K.MAX_WORLD * self.E * 4 + (32 << 20)
         self.heap = SymmetricHeap(heap_bytes or need, group=group, device=self.device)
         self.flags, self.flags_off = self.heap.alloc((K.NUM_SLOTS, K.MAX_WORLD), torch.int32)
         self.cnt_all, self.cnt_all_off = self.heap.alloc((K.MAX_WORLD, self.E), torch.int32)
@@ -168,14 +168,15 @@ class ExpertShard:
         """nn.Linear / nn.LayerNorm default initialisation, seeded per (layer, global expert) so that the same expert
         gets the same weights regardless of the number of ranks"""
         cfg = self.cfg
+        dev = self.p.device
         for le in range(self.E_loc):
-            gen = torch.Generator(device="cpu")
+            gen = torch.Generator(device=dev)
             gen.manual_seed(cfg.seed * 1000003 + layer_index * 10007 + self.first_expert + le)
             for w, b in (("w1", "b1"), ("w2", "b2"), ("w3", "b3")):
                 fan_in = self.views[w].shape[-1]
                 bound = 1.0 / math.sqrt(fan_in)
-                self.views[w][le].copy_((torch.rand(self.views[w][le].shape, generator=gen) * 2 - 1) * bound)
-                self.views[b][le].copy_((torch.rand(self.views[b][le].shape, generator=gen) * 2 - 1) * bound)
+                self.views[w][le].uniform_(-bound, bound, generator=gen)
+                self.views[b][le].uniform_(-bound, bound, generator=gen)
             for gname, bname in (("g1", "be1"), ("g2", "be2")):
                 self.views[gname][le].fill_(1.0)
                 self.views[bname][le].zero_()
@@ -301,6 +302,7 @@ class FusedDMoE(nn.Module):
             self.ws = None
         self.shard = ExpertShard(cfg, self.E_loc, self.first_expert, dev, layer_index)
         self.ref_fail_mask = None  # tests can inject an explicit failure mask into the oracle path
+        self._ref_rows = None
 
     # ------------------------------------------------------------------ public forward
     def forward(self, x):
@@ -383,17 +385,47 @@ class FusedDMoE(nn.Module):
                     group_rows=ws.group_rows, lr=cfg.lr, betas=cfg.betas, eps=cfg.eps, amsgrad=cfg.amsgrad,
                     zero_mask=SMALL_SEG_MASK)
 
+    def failure_rate_ref(self) -> float:
+        return self.cfg.failure_rate if (self.training and self.ctx is None) else 0.0
+
     # ------------------------------------------------------------------ PyTorch oracle (CPU path, tests)
     def _expert_params(self, e_local: int, dtype=torch.float32):
+        if self.ctx is None and torch.is_grad_enabled() and self.training:
+            # CPU mode: slice the flat leaf so autograd accumulates expert gradients into shard.p.grad
+            sh = self.shard
+            sh.p.requires_grad_(True)
+            out, off = {}, 0
+            for n, size in zip(SEG_NAMES, sh.seg_sizes):
+                shape = sh.views[n].shape[1:]
+                out[n] = sh.p[off + e_local * size: off + (e_local + 1) * size].view(shape)
+                off += size * sh.E_loc
+            return out
         return {n: self.shard.views[n][e_local].to(dtype) for n in SEG_NAMES}
+
+    def apply_expert_gradients_ref(self):
+        """CPU-mode counterpart of apply_expert_gradients (same per-expert AMSGrad rule, PyTorch ops)"""
+        sh, cfg = self.shard, self.cfg
+        if sh.p.grad is None or self._ref_rows is None:
+            return
+        rows = self._ref_rows
+        sh.step += (rows > 0).to(sh.step.dtype)
+        with torch.no_grad():
+            K.adam_step_ref(sh.p, sh.p.grad, sh.m, sh.v, sh.vmax, sh.seg_sizes, self.E_loc, step=sh.step,
+                            group_rows=rows, lr=cfg.lr, betas=cfg.betas, eps=cfg.eps, amsgrad=cfg.amsgrad)
+            sh.p.grad = None
+        sh.sync_bf16()
+        self._ref_rows = None
 
     def _forward_ref(self, x, logits, emulate_bf16: bool = False):
         """Dense reference of the layer: same routing, fp32 expert maths, differentiable w.r.t. x and logits only
         (expert parameters are buffers).  ``emulate_bf16`` rounds activations like the GPU path does."""
         cfg = self.cfg
+        fail_mask = self.ref_fail_mask
+        if fail_mask is None and self.failure_rate_ref() > 0:
+            fail_mask = torch.rand(x.shape[0], cfg.num_experts, device=x.device) < cfg.failure_rate
         idx, w_sel = K.gate_topk_ref(logits.detach(), self.grid_size, cfg.k,
-                                     alive=self.ctx.alive if self.ctx is not None else None,
-                                     fail_mask=self.ref_fail_mask)
+                                     alive=self.ctx.alive if self.ctx is not None else getattr(self, "alive_ref", None),
+                                     fail_mask=fail_mask)
         # differentiable weights: softmax over the selected logits
         scores = K.product_key_scores(logits, self.grid_size)
         safe_idx = idx.clamp(min=0)
@@ -403,6 +435,9 @@ class FusedDMoE(nn.Module):
         xf = x.float()
         out = torch.zeros(x.shape[0], cfg.hidden, dtype=torch.float32, device=x.device)
         rnd = (lambda t: t.to(torch.bfloat16).float()) if emulate_bf16 else (lambda t: t)
+        if self.training:
+            rows = torch.bincount(idx[idx >= 0].flatten() - self.first_expert, minlength=self.E_loc)
+            self._ref_rows = rows if self._ref_rows is None else self._ref_rows + rows
         for e in idx[idx >= 0].unique().tolist():
             le = e - self.first_expert
             p = self._expert_params(le)

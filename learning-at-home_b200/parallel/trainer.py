@@ -1,0 +1,165 @@
+"""
+``DMoETrainer`` — the public training API of the in-box engine (what ``bench.py`` and the experiments call).
+
+One trainer per rank.  It owns the flagship model of the convergence experiments (Linear -> N x DMoE -> LayerNorm ->
+Linear, reference notebook cell 2), the symmetric-heap context, and the trainer-side optimizer:
+
+* expert parameters are updated inside ``backward`` by the experts' own fused Adam (``FusedDMoE.apply_expert_gradients``)
+* the small replicated trainer parameters (stem, gates, head) live in one flat fp32 buffer whose gradient buffer sits in
+  the symmetric heap; ``lah_adam_step`` reads every rank's gradient over NVLink, averages and applies AMSGrad in ONE
+  kernel (the reference keeps per-trainer copies and never synchronises them; the emulator notebooks share them under a
+  lock — averaging is the synchronous equivalent).
+
+``train_step(x_host, y_host)`` is the end-to-end call: pinned host tensors in, python float (loss) out.
+"""
+from typing import Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from ..ops import kernels as K, native
+from .engine import DMoEConfig, EngineContext, DMoEClassifier
+
+
+class DMoETrainer:
+    def __init__(self, cfg: DMoEConfig, group=None, device: Optional[torch.device] = None):
+        self.cfg = cfg
+        self.cuda = torch.cuda.is_available() and (device is None or torch.device(device).type == "cuda")
+        if self.cuda:
+            native.have_cuda_kernels()  # loads liblah_cuda.so or raises: no silent fallback on a GPU box
+            self.ctx = EngineContext(cfg, group=group, device=device)
+            self.device = self.ctx.device
+            self.world, self.rank = self.ctx.world, self.ctx.rank
+        else:
+            self.ctx, self.device, self.world, self.rank = None, torch.device("cpu"), 1, 0
+        torch.manual_seed(cfg.seed)  # identical trainer parameters on every rank
+        self.model = DMoEClassifier(cfg, self.ctx, device=self.device).to(self.device)
+        self._flatten_trainer_params()
+        self.step_count = 0
+        B = cfg.tokens_per_rank
+        if self.cuda:
+            self._x_dev = torch.empty(B, cfg.in_features, device=self.device)
+            self._y_dev = torch.empty(B, dtype=torch.int64, device=self.device)
+            self._loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
+
+    # ------------------------------------------------------------------ trainer-side flat parameters
+    def _flatten_trainer_params(self):
+        params = [p for p in self.model.parameters()]
+        n = sum(p.numel() for p in params)
+        n_pad = (n + 3) // 4 * 4
+        dev = self.device
+        self.flat_p = torch.zeros(n_pad, device=dev)
+        if self.cuda:
+            self.flat_g, self.flat_g_off = self.ctx.heap.alloc((n_pad,), torch.float32)
+            self.flat_g.zero_()
+        else:
+            self.flat_g, self.flat_g_off = torch.zeros(n_pad), -1
+        self.flat_m, self.flat_v = torch.zeros(n_pad, device=dev), torch.zeros(n_pad, device=dev)
+        self.flat_vmax = torch.zeros(n_pad, device=dev)
+        off = 0
+        for p in params:
+            sl = slice(off, off + p.numel())
+            self.flat_p[sl].copy_(p.detach().reshape(-1))
+            p.data = self.flat_p[sl].view_as(p)
+            p.grad = self.flat_g[sl].view_as(p)
+            off += p.numel()
+        self.num_trainer_params = n
+        self._n_pad = n_pad
+        if self.cuda:
+            self.ctx.heap.barrier()
+
+    def _trainer_optimizer_step(self):
+        cfg = self.cfg
+        self.step_count += 1
+        if not self.cuda:
+            # CPU path: same maths through torch
+            if not hasattr(self, "_cpu_opt"):
+                self._cpu_opt = torch.optim.Adam([self.flat_p.requires_grad_(False)], lr=cfg.lr, betas=cfg.betas,
+                                                 eps=cfg.eps, amsgrad=cfg.amsgrad)
+            self.flat_p.grad = self.flat_g
+            self._cpu_opt.step()
+            self.flat_g.zero_()
+            return
+        c = self.ctx
+        if c.world > 1:
+            epoch = c.next_epoch()
+            K.signal_wait(c.flags_off, K.SLOT_TRAINER, epoch, c.status, signal=True, wait=True)
+            K.adam_step(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.flat_vmax, None, [self._n_pad], 1,
+                        step_scalar=self.step_count, lr=cfg.lr, betas=cfg.betas, eps=cfg.eps, amsgrad=cfg.amsgrad,
+                        world=c.world, peer_grad_off=self.flat_g_off, peer_bases=c.heap.peer_bases,
+                        grad_scale=1.0 / c.world)
+            # nobody may overwrite its gradient buffer before every peer has consumed it
+            K.signal_wait(c.flags_off, K.SLOT_BARRIER, epoch, c.status, signal=True, wait=True)
+            self.flat_g.zero_()
+        else:
+            K.adam_step(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.flat_vmax, None, [self._n_pad], 1,
+                        step_scalar=self.step_count, lr=cfg.lr, betas=cfg.betas, eps=cfg.eps, amsgrad=cfg.amsgrad,
+                        zero_mask=1)
+
+    # ------------------------------------------------------------------ steps
+    def train_step_device(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+        """one optimisation step on device tensors; returns the (device) loss tensor, no host synchronisation"""
+        self.model.train()
+        logits = self.model(x)
+        loss = F.cross_entropy(logits.float(), y)
+        loss.backward()  # expert updates happen inside (server-side semantics), trainer grads land in flat_g
+        if not self.cuda:
+            for block in self.model.blocks:
+                block.apply_expert_gradients_ref()
+        self._trainer_optimizer_step()
+        return loss.detach()
+
+    def train_step(self, x_host: torch.Tensor, y_host: torch.Tensor) -> float:
+        """END-TO-END step: host (pinned) inputs -> H2D -> fwd/bwd/optimizers -> D2H loss -> python float"""
+        if not self.cuda:
+            return float(self.train_step_device(x_host, y_host))
+        B = x_host.shape[0]
+        x, y = self._x_dev[:B], self._y_dev[:B]
+        x.copy_(x_host, non_blocking=True)
+        y.copy_(y_host, non_blocking=True)
+        loss = self.train_step_device(x, y)
+        self._loss_host.copy_(loss.reshape(1), non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return float(self._loss_host[0])
+
+    @torch.no_grad()
+    def evaluate(self, x: torch.Tensor, y: torch.Tensor):
+        self.model.eval()
+        logits = self.model(x.to(self.device))
+        y = y.to(self.device)
+        return dict(loss=float(F.cross_entropy(logits.float(), y)), acc=float((logits.argmax(-1) == y).float().mean()))
+
+    # ------------------------------------------------------------------ checkpoints
+    def state_dict(self):
+        """{'trainer': non-expert params + optimizer, 'experts': {uid: {'model': ExpertBackend-style keys,
+        'optimizer': torch Adam state_dict}}} for the experts hosted on THIS rank (shardable per rank)."""
+        from .engine import expert_uid
+        experts = {}
+        for li, block in enumerate(self.model.blocks):
+            for le in range(block.E_loc):
+                uid = f"layer{li}." + expert_uid(self.cfg, block.first_expert + le)
+                experts[uid] = dict(model=block.shard.expert_state_dict(le),
+                                    optimizer=block.shard.expert_optimizer_state(le))
+        trainer = dict(model={k: v.detach().clone().cpu() for k, v in self.model.state_dict().items()},
+                       exp_avg=self.flat_m.cpu(), exp_avg_sq=self.flat_v.cpu(), max_exp_avg_sq=self.flat_vmax.cpu(),
+                       step=self.step_count)
+        return dict(trainer=trainer, experts=experts, rng=torch.get_rng_state())
+
+    def load_state_dict(self, state):
+        from .engine import expert_uid
+        with torch.no_grad():
+            for k, v in state["trainer"]["model"].items():
+                self.model.state_dict()[k].copy_(v)
+            self.flat_m.copy_(state["trainer"]["exp_avg"])
+            self.flat_v.copy_(state["trainer"]["exp_avg_sq"])
+            self.flat_vmax.copy_(state["trainer"]["max_exp_avg_sq"])
+        self.step_count = int(state["trainer"]["step"])
+        for li, block in enumerate(self.model.blocks):
+            for le in range(block.E_loc):
+                uid = f"layer{li}." + expert_uid(self.cfg, block.first_expert + le)
+                if uid in state["experts"]:
+                    block.shard.load_expert_state_dict(le, state["experts"][uid]["model"])
+                    block.shard.load_expert_optimizer_state(le, state["experts"][uid]["optimizer"])
+        if "rng" in state:
+            torch.set_rng_state(state["rng"])
