@@ -179,7 +179,12 @@ def run_ours(args):
     sampler = ClockSampler(local_rank)
     sampler.start()
     native.reset_launches()
+    profiling = bool(os.environ.get("LAH_CUDA_PROFILE"))  # ncu --profile-from-start off
+    if profiling:
+        torch.cuda.profiler.start()
     ms = timed(step_device, args.steps, world)
+    if profiling:
+        torch.cuda.profiler.stop()
     launches = native.launches()
     clocks = sampler.stop()
     trainer.ctx.check_status()
