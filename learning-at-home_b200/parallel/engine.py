@@ -306,8 +306,12 @@ class FusedDMoE(nn.Module):
 
     # ------------------------------------------------------------------ public forward
     def forward(self, x):
+        return self.forward_with_gate(x, self.proj)
+
+    def forward_with_gate(self, x, proj: nn.Linear):
+        """run the layer with an externally owned gate (``lib.GatingFunction.proj`` on the fused in-box path)"""
         assert x.dim() == 2 and x.shape[1] == self.cfg.hidden
-        logits = F.linear(x.float(), self.proj.weight, self.proj.bias)
+        logits = F.linear(x.float(), proj.weight, proj.bias)
         if self.ctx is None:
             return self._forward_ref(x, logits)
         assert x.shape[0] <= self.cfg.tokens_per_rank, "batch exceeds DMoEConfig.tokens_per_rank"

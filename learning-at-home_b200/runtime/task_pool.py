@@ -1,0 +1,201 @@
+"""
+TaskPool — groups requests from many trainers into batches for one expert (dynamic batching across trainers).
+
+API parity with /root/reference/lib/runtime/task_pool.py:22-237 (constructor signature, ``submit_task``,
+``form_batch``, ``load_batch_to_runtime``, ``send_outputs_from_runtime``, ``priority``, ``empty``), different design:
+
+* The reference runs every pool as an OS process (2 per expert, ~131 processes per GPU) and ships batches through
+  POSIX shared memory and pipes.  Here a pool is a thread-safe in-process queue: connection-handler threads call
+  ``submit_task``, the runtime thread calls ``load_batch_to_runtime`` which forms the batch, assembles it into a
+  reusable PINNED staging buffer (native multi-threaded row gather, csrc/host_runtime.cpp) and issues ONE async H2D copy.
+* ``priority`` is the submission time of the OLDEST waiting task; the runtime serves the pool with the smallest value
+  (oldest-waiting-first).  The reference intends this but actually picks the newest (SURVEY.md §2.3 "quirk").
+* batch-size semantics are kept: greedy batches, at least ``min_batch_size`` rows, may overshoot ``max_batch_size`` by
+  the last task; with ``timeout`` set, an incomplete batch fails its tasks with TimeoutError.
+"""
+import threading
+import time
+import uuid
+from collections import deque, namedtuple
+from concurrent.futures import Future
+from typing import Any, Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from ..utils import BatchTensorProto
+
+Task = namedtuple("Task", ("future", "args", "timestamp"))
+
+
+class TaskPoolBase:
+    """Common interface between pools and TesseractRuntime (the runtime only needs these members)."""
+
+    def __init__(self, process_func: callable):
+        self.process_func = process_func
+        self._priority = float("inf")
+
+    def submit_task(self, *args: torch.Tensor) -> Future:
+        raise NotImplementedError()
+
+    def form_batch(self, *args, **kwargs) -> List[Task]:
+        raise NotImplementedError()
+
+    def iterate_minibatches(self, *args, **kwargs):
+        while True:
+            yield self.form_batch(*args, **kwargs)
+
+    @property
+    def priority(self) -> float:
+        """submission time of the oldest waiting task (smaller = more urgent); +inf when the pool is empty"""
+        return self._priority
+
+    @priority.setter
+    def priority(self, value):
+        self._priority = float(value)
+
+    @property
+    def empty(self) -> bool:
+        raise NotImplementedError()
+
+
+class TaskPool(TaskPoolBase):
+    def __init__(self, process_func: callable, inputs_schema: Tuple[BatchTensorProto, ...],
+                 outputs_schema: Tuple[BatchTensorProto, ...], max_batch_size: int, min_batch_size: int = 1,
+                 timeout: Optional[float] = None, pool_size: Optional[int] = None, prefetch_batches: int = 1,
+                 uid=None, shm_manager=None, array_headers=None, start: bool = False):
+        """
+        :param process_func: called by the runtime on every formed batch: process_func(*tensors) -> sequence of tensors
+        :param max_batch_size: stop adding tasks once a batch has this many rows (may overshoot by one task)
+        :param min_batch_size: wait for at least this many rows
+        :param timeout: seconds to wait for the next task while the batch is still below min_batch_size
+        :param pool_size: maximum number of waiting tasks; submit_task blocks when the pool is full
+        :param shm_manager, array_headers: accepted for source compatibility with the reference; unused (no shm hop)
+        """
+        super().__init__(process_func)
+        self.inputs_schema, self.outputs_schema = list(inputs_schema), list(outputs_schema)
+        self.max_batch_size, self.min_batch_size, self.timeout = max_batch_size, min_batch_size, timeout
+        self.pool_size, self.prefetch_batches = pool_size or 0, prefetch_batches
+        self.uid = uid or uuid.uuid4()
+        self._tasks = deque()
+        self._lock = threading.Lock()
+        self._not_empty = threading.Condition(self._lock)
+        self._not_full = threading.Condition(self._lock)
+        self._pending: Dict[int, List[Task]] = {}
+        self._next_batch_index = 0
+        self._staging: Dict[Tuple[int, int], torch.Tensor] = {}
+        self._alive = False
+        self.on_task = None  # set by the runtime: wakes its scheduler when a task arrives
+        if start:
+            self.start()
+
+    # ------------------------------------------------------------------ process-like lifecycle (API parity)
+    def start(self):
+        self._alive = True
+
+    def is_alive(self) -> bool:
+        return self._alive
+
+    def join(self, timeout=None):
+        self._alive = False
+
+    # ------------------------------------------------------------------ producer side (connection handlers)
+    def submit_task(self, *args: torch.Tensor) -> Future:
+        future = Future()
+        task = Task(future, args, time.time())
+        with self._lock:
+            while self.pool_size and len(self._tasks) >= self.pool_size:
+                self._not_full.wait()
+            self._tasks.append(task)
+            self._priority = self._tasks[0].timestamp
+            self._not_empty.notify()
+        if self.on_task is not None:
+            self.on_task(self)
+        return future
+
+    # ------------------------------------------------------------------ batching
+    @staticmethod
+    def get_task_size(task: Task) -> int:
+        """rows contributed by a task (the batching unit)"""
+        return len(task.args[0]) if task.args else 1
+
+    @property
+    def empty(self) -> bool:
+        return not self._tasks
+
+    def form_batch(self, block: bool = True) -> List[Task]:
+        batch, total = [], 0
+        with self._lock:
+            while total < self.max_batch_size:
+                if not self._tasks:
+                    if total >= self.min_batch_size or (not block and not batch):
+                        break
+                    if not self._not_empty.wait(self.timeout) and not self._tasks:
+                        exc = TimeoutError(f"Timeout reached but batch doesn't contain >={self.min_batch_size} elements yet.")
+                        for task in batch:
+                            task.future.set_exception(exc)
+                        raise exc
+                    continue
+                task = self._tasks.popleft()
+                if task.future.set_running_or_notify_cancel():
+                    batch.append(task)
+                    total += self.get_task_size(task)
+            self._priority = self._tasks[0].timestamp if self._tasks else float("inf")
+            self._not_full.notify_all()
+        return batch
+
+    # ------------------------------------------------------------------ runtime side
+    def _staging_buffer(self, index: int, rows: int, proto: BatchTensorProto, like: torch.Tensor, pin: bool):
+        """reusable (pinned) host buffer with capacity rounded up to a power of two, one per input slot"""
+        capacity = 1 << max(rows - 1, 0).bit_length()
+        key = (index, capacity)
+        buf = self._staging.get(key)
+        if buf is None:
+            buf = torch.empty((capacity, *like.shape[1:]), dtype=like.dtype, pin_memory=pin)
+            self._staging = {k: v for k, v in self._staging.items() if k[0] != index}  # keep one buffer per slot
+            self._staging[key] = buf
+        return buf[:rows]
+
+    def load_batch_to_runtime(self, timeout=None, device=None) -> Tuple[Any, List[torch.Tensor]]:
+        """form the next batch, assemble it and start moving it to :device:; returns (batch_index, tensors)"""
+        if timeout is not None:
+            deadline = time.time() + timeout
+            while self.empty:
+                if time.time() > deadline:
+                    raise TimeoutError()
+                time.sleep(0.0005)
+        tasks = self.form_batch()
+        batch_index = self._next_batch_index
+        self._next_batch_index += 1
+        self._pending[batch_index] = tasks
+        rows = sum(map(self.get_task_size, tasks))
+        to_cuda = device is not None and torch.device(device).type == "cuda"
+        batch = []
+        from ..ops import host
+        for i, proto in enumerate(self.inputs_schema):
+            parts = [task.args[i] for task in tasks]
+            if len(parts) == 1 and not to_cuda:
+                tensor = parts[0]
+            else:
+                staged = self._staging_buffer(i, rows, proto, parts[0], pin=to_cuda)
+                host.gather_rows(parts, staged)
+                tensor = staged
+            if device is not None:
+                tensor = tensor.to(device, non_blocking=True)
+            batch.append(tensor)
+        return batch_index, batch
+
+    def send_outputs_from_runtime(self, batch_index: int, batch_outputs: Sequence):
+        """split the outputs of a processed batch by task and resolve the tasks' futures"""
+        tasks = self._pending.pop(batch_index)
+        sizes = [self.get_task_size(task) for task in tasks]
+        outputs = [out if isinstance(out, torch.Tensor) else torch.as_tensor(out) for out in batch_outputs]
+        outputs = [out.detach().to("cpu") if out.is_cuda else out.detach() for out in outputs]
+        offset = 0
+        for task, size in zip(tasks, sizes):
+            task.future.set_result(tuple(out[offset: offset + size].clone() for out in outputs))
+            offset += size
+
+    def fail_batch(self, batch_index: int, exception: BaseException):
+        """propagate a runtime error to the authors of the batch (the reference leaves its clients hanging)"""
+        for task in self._pending.pop(batch_index, []):
+            task.future.set_exception(exception)
