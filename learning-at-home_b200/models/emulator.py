@@ -45,7 +45,9 @@ class EmulatedDMoE(nn.Module):
 
         logits = self.gating_logits(input)
         top_logits, chosen_ids = torch.topk(logits, self.num_active, dim=-1, sorted=True)
-        weights = F.softmax(top_logits, dim=-1)  # failed experts have -inf logits => zero weight
+        # failed experts have -inf logits => zero weight; a sample whose experts ALL failed gets a zero output
+        # (the reference produces NaN there: softmax over an all -inf row)
+        weights = F.softmax(top_logits, dim=-1).nan_to_num(0.0)
 
         # group (sample, slot) pairs by expert; run each used expert once on all of its tokens
         flat_ids = chosen_ids.reshape(-1)
