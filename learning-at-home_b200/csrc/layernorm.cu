@@ -123,18 +123,42 @@ __global__ void __launch_bounds__(C / 8) ln_relu_bwd_kernel(const bf16* __restri
 
     const int row0 = tile * 128;
     const int row_end = min(rows, row0 + 128);
+    // software pipeline: the loads of batch i+1 are in flight while batch i is reduced / written
+    int4 nqa[RB], nqh[RB];
+    float nmu[RB], nrs[RB];
+    auto issue_loads = [&](int rb) {
+#pragma unroll
+        for (int r = 0; r < RB; ++r) {
+            const int row = rb + r;
+            const int rr = row < row_end ? row : row0;
+            const long long off = static_cast<long long>(rr) * C + col;
+            nqa[r] = ld_nc_v4(reinterpret_cast<const int4*>(da + off));
+            nqh[r] = ld_nc_v4(reinterpret_cast<const int4*>(h + off));
+            nmu[r] = __ldg(mean_in + rr);
+            nrs[r] = __ldg(rstd_in + rr);
+        }
+    };
+    issue_loads(row0);
     for (int rb = row0; rb < row_end; rb += RB) {
         float gv[RB][8], xh[RB][8], rs[RB];
         float part[2 * RB];
+        int4 qa_c[RB], qh_c[RB];
+        float mu_c[RB];
+#pragma unroll
+        for (int r = 0; r < RB; ++r) {
+            qa_c[r] = nqa[r];
+            qh_c[r] = nqh[r];
+            mu_c[r] = nmu[r];
+            rs[r] = nrs[r];
+        }
+        if (rb + RB < row_end) issue_loads(rb + RB);
 #pragma unroll
         for (int r = 0; r < RB; ++r) {
             const int row = rb + r;
             const bool ok = row < row_end;
-            const long long off = static_cast<long long>(ok ? row : row0) * C + col;
-            const int4 qa = ld_nc_v4(reinterpret_cast<const int4*>(da + off));
-            const int4 qh = ld_nc_v4(reinterpret_cast<const int4*>(h + off));
-            const float mu = __ldg(mean_in + (ok ? row : row0));
-            rs[r] = __ldg(rstd_in + (ok ? row : row0));
+            const int4 qa = qa_c[r];
+            const int4 qh = qh_c[r];
+            const float mu = mu_c[r];
             const uint32_t wa[4] = {(uint32_t)qa.x, (uint32_t)qa.y, (uint32_t)qa.z, (uint32_t)qa.w};
             const uint32_t wh[4] = {(uint32_t)qh.x, (uint32_t)qh.y, (uint32_t)qh.z, (uint32_t)qh.w};
             float s1 = 0.f, s2 = 0.f;

@@ -193,6 +193,7 @@ struct LayoutArgs {
     int E, E_loc;
     int max_rows;            // capacity of the receive buffers (rows)
     int max_tiles;           // max_rows / 128
+    int align;               // group padding in rows: 128 (1-CTA GEMM) or 256 (CTA-pair GEMM)
     int* counts;             // [E] local counts (zeroed on exit)
     int* dst_row;            // [E]  row in the owner's buffer where MY first row for expert e goes
     int* group_off;          // [E_loc + 1] padded offsets of my local experts
@@ -238,7 +239,7 @@ __global__ void __launch_bounds__(1024) layout_exchange_kernel(Peers peers, Layo
                 if (s < me) before += c;
             }
         }
-        const int padded = (tot + 127) & ~127;
+        const int padded = (tot + a.align - 1) / a.align * a.align;
         int v = padded;  // inclusive scan inside the warp
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -278,7 +279,7 @@ __global__ void __launch_bounds__(1024) layout_exchange_kernel(Peers peers, Layo
         if (owner == me) {
             const int le = e - me * a.E_loc;
             a.group_off[le] = rel;
-            const int padded = (a.group_rows[le] + 127) & ~127;
+            const int padded = (a.group_rows[le] + a.align - 1) / a.align * a.align;
             for (int t = rel / 128; t < (rel + padded) / 128 && t < a.max_tiles; ++t) a.tile_group[t] = le;
         }
         a.dst_row[e] = rel + before;
@@ -311,6 +312,7 @@ struct ScatterArgs {
     const int* group_off;     // local experts (for zero padding)
     const int* group_rows;
     int pair_blocks;          // CTAs that handle pairs; the rest zero padding
+    int align;                // group padding in rows
     int* done_counter;
     int* status;
 };
@@ -363,7 +365,7 @@ __global__ void __launch_bounds__(256) scatter_rows_kernel(Peers peers, ScatterA
         const int4 z = make_int4(0, 0, 0, 0);
         for (int le = blockIdx.x - a.pair_blocks; le < a.E_loc; le += nb) {
             const int r0 = a.group_off[le] + a.group_rows[le];
-            const int r1 = min(a.max_rows, (a.group_off[le] + ((a.group_rows[le] + 127) & ~127)));
+            const int r1 = min(a.max_rows, a.group_off[le] + (a.group_rows[le] + a.align - 1) / a.align * a.align);
             for (int r = r0 + warp; r < r1; r += 8) {
                 int4* dp = base + static_cast<long long>(r) * (a.H / 8);
 #pragma unroll
@@ -588,12 +590,12 @@ int lah_gate_topk(const float* logits, int B, const int* grid, int ndim, int k, 
 }
 
 int lah_layout_exchange(long long cnt_all_off, long long flags_off, int slot, int epoch, int E, int E_loc, int max_rows,
-                        int* counts, int* dst_row, int* group_off, int* group_rows, int* tile_group, int* total_rows,
+                        int align, int* counts, int* dst_row, int* group_off, int* group_rows, int* tile_group, int* total_rows,
                         int* status, cudaStream_t st) {
     if (!g_peers_set) return -10;
     LayoutArgs a;
     a.cnt_all_off = cnt_all_off; a.flags_off = flags_off; a.slot = slot; a.epoch = epoch; a.E = E; a.E_loc = E_loc;
-    a.max_rows = max_rows; a.max_tiles = max_rows / 128; a.counts = counts; a.dst_row = dst_row; a.group_off = group_off;
+    a.max_rows = max_rows; a.max_tiles = max_rows / 128; a.align = align; a.counts = counts; a.dst_row = dst_row; a.group_off = group_off;
     a.group_rows = group_rows; a.tile_group = tile_group; a.total_rows = total_rows; a.status = status;
     layout_exchange_kernel<<<1, 1024, 0, st>>>(g_peers, a);
     return -(int)cudaGetLastError();
@@ -601,14 +603,14 @@ int lah_layout_exchange(long long cnt_all_off, long long flags_off, int slot, in
 
 int lah_scatter_rows(const void* src, const float* scale, const int* idx, const int* pos, const int* dst_row,
                      int* pair_row, long long dst_off, long long flags_off, int slot, int epoch, int num_pairs, int k,
-                     int H, int E_loc, int max_rows, const int* group_off, const int* group_rows, int* done_counter,
-                     int* status, cudaStream_t st) {
+                     int H, int E_loc, int max_rows, int align, const int* group_off, const int* group_rows,
+                     int* done_counter, int* status, cudaStream_t st) {
     if (!g_peers_set) return -10;
     ScatterArgs a;
     a.src = (const bf16*)src; a.scale = scale; a.idx = idx; a.pos = pos; a.dst_row = dst_row; a.pair_row = pair_row;
     a.dst_off = dst_off; a.flags_off = flags_off; a.slot = slot; a.epoch = epoch; a.num_pairs = num_pairs; a.k = k;
     a.H = H; a.E_loc = E_loc; a.max_rows = max_rows; a.group_off = group_off; a.group_rows = group_rows;
-    a.pair_blocks = (num_pairs + 7) / 8; a.done_counter = done_counter; a.status = status;
+    a.pair_blocks = (num_pairs + 7) / 8; a.align = align; a.done_counter = done_counter; a.status = status;
     const int pad_blocks = E_loc < 64 ? E_loc : 64;
     const int grid = a.pair_blocks + pad_blocks;
     if (H == 256) scatter_rows_kernel<1><<<grid, 256, 0, st>>>(g_peers, a);

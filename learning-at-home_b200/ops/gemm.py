@@ -31,6 +31,12 @@ def _lib():
         lib.lah_gemm_kgroup.restype = c_int
         lib.lah_gemm_kgroup.argtypes = [c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p,
                                         c_void_p, c_ll, c_ll, c_int, c_int, c_void_p]
+        lib.lah_gemm_mgroup2.restype = c_int
+        lib.lah_gemm_mgroup2.argtypes = [c_void_p, c_ll, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_ll,
+                                         c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_void_p]
+        lib.lah_gemm_kgroup2.restype = c_int
+        lib.lah_gemm_kgroup2.argtypes = [c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p,
+                                         c_void_p, c_ll, c_ll, c_int, c_void_p]
         _configured = True
     return lib
 
@@ -44,7 +50,7 @@ def _pick_block_n(n: int) -> int:
 
 
 def grouped_linear(a, w, *, tile_group=None, bias=None, residual=None, w_is_kn=False, out=None,
-                   out_dtype=torch.bfloat16, m_valid=None, block_n=None, max_ctas=0):
+                   out_dtype=torch.bfloat16, m_valid=None, block_n=None, max_ctas=0, two_cta=False):
     """
     out[r, :] = a[r, :] @ W[g(r)]^T (+ bias[g(r)]) (+ residual[r, :])
 
@@ -73,6 +79,15 @@ def grouped_linear(a, w, *, tile_group=None, bias=None, residual=None, w_is_kn=F
         assert bias.dtype == torch.float32 and bias.is_contiguous() and bias.numel() == G * N
     if residual is not None:
         assert residual.dtype == torch.bfloat16 and residual.stride(1) == 1
+    if two_cta and N % 256 == 0:
+        # CTA-pair kernel (cta_group::2, 256x256 tiles): expert groups must be padded to 256 rows
+        code = _lib().lah_gemm_mgroup2(
+            ptr(a), a.stride(0), rows, ptr(w), G, N, K, int(w_is_kn), ptr(out), out.stride(0),
+            int(out.dtype == torch.float32), rows if m_valid is None else m_valid, num_m_tiles, ptr(tile_group),
+            ptr(bias), ptr(residual), residual.stride(0) if residual is not None else 0, max_ctas, stream_ptr())
+        native.check(code, "lah_gemm_mgroup2")
+        native.count_launch()
+        return out
     bn = block_n or _pick_block_n(N)
     code = _lib().lah_gemm_mgroup(
         ptr(a), a.stride(0), rows, ptr(w), G, N, K, int(w_is_kn), ptr(out), out.stride(0),
@@ -83,7 +98,7 @@ def grouped_linear(a, w, *, tile_group=None, bias=None, residual=None, w_is_kn=F
     return out
 
 
-def grouped_wgrad(dy, x, group_off, num_groups, *, out=None, block_n=None, max_ctas=0):
+def grouped_wgrad(dy, x, group_off, num_groups, *, out=None, block_n=None, max_ctas=0, two_cta=False):
     """
     out[g] = dy[off[g]:off[g+1]]^T @ x[off[g]:off[g+1]]   (fp32 [G, M, N]); groups with no rows are left untouched.
     The reduction over an expert's rows IS the gradient reduction over all trainers that routed tokens to it.
@@ -96,6 +111,12 @@ def grouped_wgrad(dy, x, group_off, num_groups, *, out=None, block_n=None, max_c
     if out is None:
         out = torch.zeros(num_groups, M, N, device=dy.device, dtype=torch.float32)
     assert out.dtype == torch.float32 and out.is_contiguous()
+    if two_cta and M % 256 == 0 and N % 256 == 0:
+        code = _lib().lah_gemm_kgroup2(ptr(dy), dy.stride(0), ptr(x), x.stride(0), rows, num_groups, M, N,
+                                       ptr(group_off), ptr(out), N, M * N, max_ctas, stream_ptr())
+        native.check(code, "lah_gemm_kgroup2")
+        native.count_launch()
+        return out
     bn = block_n or _pick_block_n(N)
     code = _lib().lah_gemm_kgroup(ptr(dy), dy.stride(0), ptr(x), x.stride(0), rows, num_groups, M, N, ptr(group_off),
                                   ptr(out), N, M * N, bn, max_ctas, stream_ptr())

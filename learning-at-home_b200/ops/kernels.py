@@ -31,8 +31,8 @@ def _lib():
         "lah_grouped_colsum": [P, L, P, I, P, I, P],
         "lah_set_peers": [P, I, I],
         "lah_gate_topk": [P, I, P, I, I, P, Fl, c_ull, L, P, P, P, P, P],
-        "lah_layout_exchange": [L, L, I, I, I, I, I, P, P, P, P, P, P, P, P],
-        "lah_scatter_rows": [P, P, P, P, P, P, L, L, I, I, I, I, I, I, I, P, P, P, P, P],
+        "lah_layout_exchange": [L, L, I, I, I, I, I, I, P, P, P, P, P, P, P, P],
+        "lah_scatter_rows": [P, P, P, P, P, P, L, L, I, I, I, I, I, I, I, I, P, P, P, P, P],
         "lah_signal_wait": [L, I, I, I, I, P, P],
         "lah_combine_rows": [L, P, P, P, P, I, I, I, I, P],
         "lah_gate_bwd": [L, P, P, P, P, P, I, I, I, I, P, I, P],
@@ -105,21 +105,21 @@ def gate_topk(logits, grid_size, k, *, alive=None, failure_rate=0.0, seed=0, tok
     native.count_launch()
 
 
-def layout_exchange(cnt_all_off, flags_off, slot, epoch, E, E_loc, max_rows, *, counts, dst_row, group_off, group_rows,
+def layout_exchange(cnt_all_off, flags_off, slot, epoch, E, E_loc, max_rows, *, align=128, counts, dst_row, group_off, group_rows,
                     tile_group, total_rows, status):
-    native.check(_lib().lah_layout_exchange(cnt_all_off, flags_off, slot, epoch, E, E_loc, max_rows, ptr(counts),
+    native.check(_lib().lah_layout_exchange(cnt_all_off, flags_off, slot, epoch, E, E_loc, max_rows, align, ptr(counts),
                                             ptr(dst_row), ptr(group_off), ptr(group_rows), ptr(tile_group),
                                             ptr(total_rows), ptr(status), stream_ptr()), "lah_layout_exchange")
     native.count_launch()
 
 
 def scatter_rows(src, scale, idx, pos, dst_row, pair_row, dst_off, flags_off, slot, epoch, k, E_loc, max_rows,
-                 group_off, group_rows, done_counter, status):
+                 group_off, group_rows, done_counter, status, align=128):
     num_pairs = idx.numel()
     H = src.shape[1]
     assert src.is_contiguous() and src.dtype == torch.bfloat16
     native.check(_lib().lah_scatter_rows(ptr(src), ptr(scale), ptr(idx), ptr(pos), ptr(dst_row), ptr(pair_row), dst_off,
-                                         flags_off, slot, epoch, num_pairs, k, H, E_loc, max_rows, ptr(group_off),
+                                         flags_off, slot, epoch, num_pairs, k, H, E_loc, max_rows, align, ptr(group_off),
                                          ptr(group_rows), ptr(done_counter), ptr(status), stream_ptr()),
                  "lah_scatter_rows")
     native.count_launch()

@@ -52,6 +52,7 @@ class DMoEConfig:
     amsgrad: bool = True
     seed: int = 1337
     uid_prefix: str = "expert"
+    two_cta: bool = True                 # CTA-pair (cta_group::2, 256x256 tiles) GEMMs; expert groups padded to 256 rows
 
     @property
     def num_experts(self) -> int:
@@ -95,7 +96,11 @@ class EngineContext:
         self.E_loc = self.E // self.world
         pairs = cfg.tokens_per_rank * cfg.k
         cap = pairs if self.world == 1 else int(math.ceil(pairs * cfg.capacity_factor))
-        self.max_rows = ((cap + 127) // 128 + self.E_loc) * 128
+        import os
+        self.two_cta = cfg.two_cta and os.environ.get("LAH_TWO_CTA", "1") != "0" and cfg.inner % 256 == 0 \
+            and cfg.hidden % 256 == 0
+        self.align = 256 if self.two_cta else 128   # expert groups are padded to this many rows
+        self.max_rows = ((cap + self.align - 1) // self.align + self.E_loc) * self.align
         self.max_tiles = self.max_rows // 128
         H = cfg.hidden
         sym_rows_bytes = self.max_rows * H * 2
@@ -328,20 +333,22 @@ class FusedDMoE(nn.Module):
                     seed=cfg.seed * 7919 + self.layer_index, token_offset=c.token_counter, idx=idx, w=w, pos=pos,
                     counts=c.counts)
         c.token_counter += B
-        K.layout_exchange(c.cnt_all_off, c.flags_off, K.SLOT_COUNTS, epoch, c.E, c.E_loc, c.max_rows, counts=c.counts,
+        K.layout_exchange(c.cnt_all_off, c.flags_off, K.SLOT_COUNTS, epoch, c.E, c.E_loc, c.max_rows, align=c.align,
+                          counts=c.counts,
                           dst_row=ws.dst_row, group_off=ws.group_off, group_rows=ws.group_rows,
                           tile_group=ws.tile_group, total_rows=ws.total_rows, status=c.status)
         K.scatter_rows(x, None, idx, pos, ws.dst_row, pair_row, ws.xd_off, c.flags_off, K.SLOT_DISPATCH, epoch, k,
-                       c.E_loc, c.max_rows, ws.group_off, ws.group_rows, c.done_counter, c.status)
+                       c.E_loc, c.max_rows, ws.group_off, ws.group_rows, c.done_counter, c.status, align=c.align)
         if c.world > 1:
             K.signal_wait(c.flags_off, K.SLOT_DISPATCH, epoch, c.status, signal=False, wait=True)
         # ---- expert FFN on the rows this rank received (grouped by expert)
         tg = ws.tile_group
-        gemm.grouped_linear(ws.xd, sh.bf16["w1"], tile_group=tg, bias=sh.views["b1"], out=ws.h1)
+        gemm.grouped_linear(ws.xd, sh.bf16["w1"], tile_group=tg, bias=sh.views["b1"], out=ws.h1, two_cta=c.two_cta)
         K.ln_relu_fwd(ws.h1, sh.views["g1"], sh.views["be1"], tg, out=ws.a1, mean=ws.mean1, rstd=ws.rstd1)
-        gemm.grouped_linear(ws.a1, sh.bf16["w2"], tile_group=tg, bias=sh.views["b2"], out=ws.h2)
+        gemm.grouped_linear(ws.a1, sh.bf16["w2"], tile_group=tg, bias=sh.views["b2"], out=ws.h2, two_cta=c.two_cta)
         K.ln_relu_fwd(ws.h2, sh.views["g2"], sh.views["be2"], tg, out=ws.a2, mean=ws.mean2, rstd=ws.rstd2)
-        gemm.grouped_linear(ws.a2, sh.bf16["w3"], tile_group=tg, bias=sh.views["b3"], residual=ws.xd, out=ws.yo)
+        gemm.grouped_linear(ws.a2, sh.bf16["w3"], tile_group=tg, bias=sh.views["b3"], residual=ws.xd, out=ws.yo,
+                            two_cta=c.two_cta)
         if c.world > 1:
             K.signal_wait(c.flags_off, K.SLOT_OUTPUT, epoch, c.status, signal=True, wait=True)
         y = torch.empty(B, cfg.hidden, dtype=torch.bfloat16, device=x.device)
@@ -358,22 +365,23 @@ class FusedDMoE(nn.Module):
         dlogits = torch.empty(B, sum(self.grid_size), dtype=torch.float32, device=gy.device)
         K.gate_bwd(ws.yo_off, gy, idx, pair_row, w, dlogits, k, c.E_loc, self.grid_size)
         K.scatter_rows(gy, w, idx, pos, None, pair_row, c.gyd_off, c.flags_off, K.SLOT_GRAD, epoch, k, c.E_loc,
-                       c.max_rows, ws.group_off, ws.group_rows, c.done_counter, c.status)
+                       c.max_rows, ws.group_off, ws.group_rows, c.done_counter, c.status, align=c.align)
         if c.world > 1:
             K.signal_wait(c.flags_off, K.SLOT_GRAD, epoch, c.status, signal=False, wait=True)
         tg, go, G = ws.tile_group, ws.group_off, c.E_loc
         gr = sh.grads
         K.grouped_colsum(c.gyd, tg, out=gr["b3"])
-        gemm.grouped_wgrad(c.gyd, ws.a2, go, G, out=gr["w3"])
-        gemm.grouped_linear(c.gyd, sh.bf16["w3"], tile_group=tg, w_is_kn=True, out=c.da)
+        gemm.grouped_wgrad(c.gyd, ws.a2, go, G, out=gr["w3"], two_cta=c.two_cta)
+        gemm.grouped_linear(c.gyd, sh.bf16["w3"], tile_group=tg, w_is_kn=True, out=c.da, two_cta=c.two_cta)
         K.ln_relu_bwd(c.da, ws.h2, ws.mean2, ws.rstd2, sh.views["g2"], sh.views["be2"], tg, dh=c.dh, dgamma=gr["g2"],
                       dbeta=gr["be2"], dbias=gr["b2"])
-        gemm.grouped_wgrad(c.dh, ws.a1, go, G, out=gr["w2"])
-        gemm.grouped_linear(c.dh, sh.bf16["w2"], tile_group=tg, w_is_kn=True, out=c.da)
+        gemm.grouped_wgrad(c.dh, ws.a1, go, G, out=gr["w2"], two_cta=c.two_cta)
+        gemm.grouped_linear(c.dh, sh.bf16["w2"], tile_group=tg, w_is_kn=True, out=c.da, two_cta=c.two_cta)
         K.ln_relu_bwd(c.da, ws.h1, ws.mean1, ws.rstd1, sh.views["g1"], sh.views["be1"], tg, dh=c.dh, dgamma=gr["g1"],
                       dbeta=gr["be1"], dbias=gr["b1"])
-        gemm.grouped_wgrad(c.dh, ws.xd, go, G, out=gr["w1"])
-        gemm.grouped_linear(c.dh, sh.bf16["w1"], tile_group=tg, w_is_kn=True, residual=c.gyd, out=c.dxd)
+        gemm.grouped_wgrad(c.dh, ws.xd, go, G, out=gr["w1"], two_cta=c.two_cta)
+        gemm.grouped_linear(c.dh, sh.bf16["w1"], tile_group=tg, w_is_kn=True, residual=c.gyd, out=c.dxd,
+                            two_cta=c.two_cta)
         # ---- expert-side optimizer step (reference: ExpertBackend.apply_gradients right after backward)
         self.apply_expert_gradients()
         if c.world > 1:

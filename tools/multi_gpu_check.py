@@ -25,6 +25,7 @@ def main():
     B = 256
     cfg = E.DMoEConfig(hidden=512, grid_size=(4, 4), k=4, num_layers=1, tokens_per_rank=B, capacity_factor=4.0)
     ctx = E.EngineContext(cfg)
+    torch.manual_seed(0)  # identical gate on every rank (DMoETrainer does the same)
     layer = E.FusedDMoE(cfg, ctx).cuda()
     gen = torch.Generator().manual_seed(0)
     x_all = torch.randn(world * B, 512, generator=gen).to(torch.bfloat16)
