@@ -33,14 +33,17 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--batch-per-gpu", type=int, default=32768, help="samples per GPU per step (weak scaling)")
+    ap.add_argument("--batch-per-gpu", type=int, default=65536, help="samples per GPU per step (weak scaling)")
     ap.add_argument("--ref-batch", type=int, default=64, help="samples per step for the reference arm")
     ap.add_argument("--hidden", type=int, default=512)
-    ap.add_argument("--grid", type=int, nargs="+", default=[8, 8])
+    ap.add_argument("--grid", type=int, nargs="+", default=[64])
+    ap.add_argument("--gate", choices=["emulator", "product_key"], default="emulator",
+                    help="emulator = EmulatedDMoE gate of the reference arm (LayerNorm + normalized keys, not trained)")
     ap.add_argument("--layers", type=int, default=4)
     ap.add_argument("--k", type=int, default=4)
     ap.add_argument("--failure-rate", type=float, default=0.0)
-    ap.add_argument("--capacity-factor", type=float, default=2.0)
+    ap.add_argument("--capacity-factor", type=float, default=0.0,
+                    help="receive-buffer rows / local (token, expert) pairs; 0 = auto (retry with a larger one on overflow)")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
 
@@ -155,8 +158,37 @@ def run_ours(args):
     from lah_b200.parallel.trainer import DMoETrainer
 
     B = args.batch_per_gpu
+    # Expert load is imbalanced by nature (deep layers route most tokens through a few hot experts), so the rank hosting a
+    # hot expert receives far more than its share of rows.  Nothing is ever dropped: if a receive buffer overflows the
+    # engine raises, and we re-run the WHOLE measurement with bigger buffers.
+    factors = [args.capacity_factor] if args.capacity_factor > 0 else [f for f in (3.0, 5.0, float(world)) if f <= max(world, 3)]
+    for attempt, factor in enumerate(factors):
+        try:
+            _measure_ours(args, rank, world, local_rank, B, factor)
+            break
+        except RuntimeError as e:
+            if "overflow" not in str(e) or attempt == len(factors) - 1:
+                raise
+            if rank == 0:
+                print(f"[bench] receive buffers overflowed at capacity_factor={factor}; retrying with {factors[attempt + 1]}",
+                      file=sys.stderr)
+            import gc
+            gc.collect()
+            torch.cuda.empty_cache()
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def _measure_ours(args, rank, world, local_rank, B, capacity_factor):
+    import lah_b200  # noqa
+    from lah_b200.ops import native
+    from lah_b200.parallel.engine import DMoEConfig
+    from lah_b200.parallel.trainer import DMoETrainer
     cfg = DMoEConfig(hidden=args.hidden, grid_size=tuple(args.grid), k=args.k, num_layers=args.layers,
-                     tokens_per_rank=B, capacity_factor=args.capacity_factor, failure_rate=args.failure_rate)
+                     tokens_per_rank=B, capacity_factor=capacity_factor, failure_rate=args.failure_rate,
+                     gate_mode=args.gate)
     trainer = DMoETrainer(cfg)
     gen = torch.Generator().manual_seed(1234 + rank)
     n_batches = 4
@@ -173,9 +205,23 @@ def run_ours(args):
     def step_e2e(i):
         losses.append(trainer.train_step(xs_host[i % n_batches], ys_host[i % n_batches]))
 
+    def check_all_ranks():
+        code = int(trainer.ctx.status.item())
+        if world > 1:
+            import torch.distributed as dist
+            t = torch.tensor([code], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.BOR)
+            code = int(t.item())
+        if code:
+            trainer.ctx.status.fill_(code)
+            try:
+                trainer.ctx.check_status()
+            finally:
+                trainer.ctx.heap.close()
+
     for i in range(args.warmup):
         step_device(i)
-    trainer.ctx.check_status()
+    check_all_ranks()
     sampler = ClockSampler(local_rank)
     sampler.start()
     native.reset_launches()
@@ -187,7 +233,7 @@ def run_ours(args):
         torch.cuda.profiler.stop()
     launches = native.launches()
     clocks = sampler.stop()
-    trainer.ctx.check_status()
+    check_all_ranks()
     global_batch = B * world
     value = global_batch * args.steps / (ms / 1e3)
 
@@ -196,12 +242,17 @@ def run_ours(args):
         for i in range(2):
             step_e2e(i)
         ms_e2e = timed(step_e2e, args.steps, world)
-        trainer.ctx.check_status()
+        check_all_ranks()
         e2e = {"value": global_batch * args.steps / (ms_e2e / 1e3), "unit": "samples/s",
                "ms_per_step": ms_e2e / args.steps,
                "h2d_bytes_per_step": int(xs_host[0].numel() * 4 + ys_host[0].numel() * 8),
                "d2h_bytes_per_step": 4, "last_loss": losses[-1] if losses else None}
 
+    routing = []
+    for block in trainer.model.blocks:  # tokens-per-expert histogram of the last step (observability)
+        rows = block.ws.group_rows.float()
+        routing.append({"active_experts": int((rows > 0).sum()), "max_rows": int(rows.max()), "mean_rows": float(rows.mean()),
+                        "padded_rows": int(block.ws.total_rows.item())})
     if rank == 0:
         out = {
             "metric": "DMoE training samples/sec (whole job, device-timed, max over ranks)",
@@ -212,16 +263,15 @@ def run_ours(args):
                                 f"FeedforwardBlock({cfg.hidden}), top-{cfg.k}] -> LayerNorm -> Linear({cfg.hidden},10); "
                                 "fwd+bwd+per-expert AMSGrad+trainer AMSGrad",
                        "global_batch": global_batch, "seq_len": 1, "parallelism": f"ep{world}+dp{world}",
+                       "capacity_factor": capacity_factor,
                        "experts_total": cfg.num_experts * cfg.num_layers, "failure_rate": cfg.failure_rate,
+                       "gate": cfg.gate_mode + (" (LayerNorm(x) @ normalize(keys); gate params not trained, exactly like the reference's EmulatedDMoE)" if cfg.gate_mode == "emulator" else " (trainable product-key proj, lib.GatingFunction)"),
                        "l2_policy": "working set per step (>35 GB of expert state + >10 GB activations) exceeds the 126 MB L2; no explicit flush"},
-            "clocks": clocks, "gpu_launches": launches, "e2e": e2e,
+            "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "routing_rank0": routing,
             "baseline_note": "vs_baseline = value / 16.8 samples/s (reference notebook dmoe64x4, BASELINE.md)",
         }
         print(json.dumps(out))
-    if world > 1:
-        import torch.distributed as dist
-        dist.barrier()
-        dist.destroy_process_group()
+    return True
 
 
 # ------------------------------------------------------------------------------------------------ reference arm

@@ -53,6 +53,12 @@ class DMoEConfig:
     seed: int = 1337
     uid_prefix: str = "expert"
     two_cta: bool = True                 # CTA-pair (cta_group::2, 256x256 tiles) GEMMs; expert groups padded to 256 rows
+    # gate of the fused layer:
+    #   "product_key": lib.GatingFunction semantics — trainable proj = Linear(hidden, sum(grid)), score = sum of per-dim logits
+    #   "emulator":    EmulatedDMoE semantics (dmoe_emulator.py:47) — logits = LayerNorm(x) @ F.normalize(expert_keys, -1);
+    #                  like in the reference emulator these gate parameters are NOT trained (get_non_expert_params excludes
+    #                  them and no expert optimizer owns them); requires a 1-d grid (grid_size=(num_experts,))
+    gate_mode: str = "product_key"
 
     @property
     def num_experts(self) -> int:
@@ -298,7 +304,14 @@ class FusedDMoE(nn.Module):
         super().__init__()
         self.cfg, self.ctx, self.layer_index = cfg, ctx, layer_index
         self.grid_size = tuple(cfg.grid_size)
-        self.proj = nn.Linear(cfg.hidden, sum(cfg.grid_size))
+        if cfg.gate_mode == "emulator":
+            assert len(self.grid_size) == 1, "gate_mode='emulator' scores experts densely: use grid_size=(num_experts,)"
+            self.gating_pre_normalize = nn.LayerNorm(cfg.hidden)
+            self.expert_keys = nn.Parameter(torch.randn(cfg.hidden, cfg.num_experts), requires_grad=False)
+            self.gating_pre_normalize.requires_grad_(False)
+            self.proj = None
+        else:
+            self.proj = nn.Linear(cfg.hidden, sum(cfg.grid_size))
         if ctx is not None:
             self.E_loc, self.first_expert, dev = ctx.E_loc, ctx.rank * ctx.E_loc, ctx.device
             self.ws = LayerWorkspace(ctx)
@@ -313,10 +326,15 @@ class FusedDMoE(nn.Module):
     def forward(self, x):
         return self.forward_with_gate(x, self.proj)
 
-    def forward_with_gate(self, x, proj: nn.Linear):
+    def gate_logits(self, x, proj=None):
+        if self.cfg.gate_mode == "emulator" and proj is None:
+            return self.gating_pre_normalize(x.float()) @ F.normalize(self.expert_keys, dim=-1)
+        return F.linear(x.float(), proj.weight, proj.bias)
+
+    def forward_with_gate(self, x, proj: Optional[nn.Linear]):
         """run the layer with an externally owned gate (``lib.GatingFunction.proj`` on the fused in-box path)"""
         assert x.dim() == 2 and x.shape[1] == self.cfg.hidden
-        logits = F.linear(x.float(), proj.weight, proj.bias)
+        logits = self.gate_logits(x, proj)
         if self.ctx is None:
             return self._forward_ref(x, logits)
         assert x.shape[0] <= self.cfg.tokens_per_rank, "batch exceeds DMoEConfig.tokens_per_rank"

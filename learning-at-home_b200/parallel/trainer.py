@@ -45,7 +45,7 @@ class DMoETrainer:
 
     # ------------------------------------------------------------------ trainer-side flat parameters
     def _flatten_trainer_params(self):
-        params = [p for p in self.model.parameters()]
+        params = [p for p in self.model.parameters() if p.requires_grad]  # a frozen (emulator-style) gate stays out
         n = sum(p.numel() for p in params)
         n_pad = (n + 3) // 4 * 4
         dev = self.device
