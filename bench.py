@@ -161,7 +161,12 @@ def run_ours(args):
     # Expert load is imbalanced by nature (deep layers route most tokens through a few hot experts), so the rank hosting a
     # hot expert receives far more than its share of rows.  Nothing is ever dropped: if a receive buffer overflows the
     # engine raises, and we re-run the WHOLE measurement with bigger buffers.
-    factors = [args.capacity_factor] if args.capacity_factor > 0 else [f for f in (3.0, 5.0, float(world)) if f <= max(world, 3)]
+    if args.capacity_factor > 0:
+        factors = [args.capacity_factor]
+    elif os.environ.get("LAH_BENCH_FACTORS"):
+        factors = [float(f) for f in os.environ["LAH_BENCH_FACTORS"].split(",")]
+    else:
+        factors = sorted({min(3.0, float(world)), min(5.0, float(world)), float(world)})
     for attempt, factor in enumerate(factors):
         try:
             _measure_ours(args, rank, world, local_rank, B, factor)
@@ -209,9 +214,9 @@ def _measure_ours(args, rank, world, local_rank, B, capacity_factor):
         code = int(trainer.ctx.status.item())
         if world > 1:
             import torch.distributed as dist
-            t = torch.tensor([code], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.BOR)
-            code = int(t.item())
+            t = torch.tensor([code & 1, code & 2], device="cuda")  # NCCL has no bitwise-or: MAX per status bit
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            code = int(t[0].item()) | int(t[1].item())
         if code:
             trainer.ctx.status.fill_(code)
             try:
