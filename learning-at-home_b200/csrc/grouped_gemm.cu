@@ -41,6 +41,10 @@ struct GemmParams {
     const float* bias;         // MGROUP: [G, N] or nullptr
     const bf16* residual;      // MGROUP: [rows, ldr] or nullptr
     long long ldr;
+    // receive-side fusion: the TMA producer waits until every source rank's dispatch flag reached `wait_epoch`
+    const int* wait_flags;     // [wait_count] local flag words written by the peers (st.release.sys), or nullptr
+    int wait_count, wait_epoch;
+    int* status;
 };
 
 template <int BLOCK_N, int STAGES>
@@ -124,6 +128,11 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA, const _
 
     if (warp == 0 && lane == 0) {
         // =============================================================== TMA producer
+        if (p.wait_flags) {  // rows pushed by peer GPUs over NVLink must have landed before the first TMA load
+            for (int sidx = 0; sidx < p.wait_count; ++sidx)
+                if (!spin_flag_ge(p.wait_flags + sidx, p.wait_epoch)) atomicOr(p.status, 1);
+            fence_proxy_async_global();
+        }
         int stage = 0;
         uint32_t phase = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -379,7 +388,7 @@ extern "C" {
 int lah_gemm_mgroup(const void* A, long long lda, int a_rows, const void* B, int G, int N, int K, int b_mn, void* C,
                     long long ldc, int out_f32, int m_valid, int num_m_tiles, const int* tile_group,
                     const float* bias, const void* residual, long long ldr, int block_n, int max_ctas,
-                    cudaStream_t stream) {
+                    const int* wait_flags, int wait_count, int wait_epoch, int* status, cudaStream_t stream) {
     if ((K % 8) || (N % 32) || (lda % 8)) return -2;
     CUtensorMap tmA, tmB;
     {
@@ -406,6 +415,7 @@ int lah_gemm_mgroup(const void* A, long long lda, int a_rows, const void* B, int
     p.N = N; p.K = K; p.M = m_valid; p.num_groups = G; p.num_m_tiles = num_m_tiles; p.tile_group = tile_group;
     p.group_off = nullptr; p.C = C; p.ldc = ldc; p.c_group_stride = 0; p.bias = bias;
     p.residual = reinterpret_cast<const bf16*>(residual); p.ldr = ldr;
+    p.wait_flags = wait_flags; p.wait_count = wait_count; p.wait_epoch = wait_epoch; p.status = status;
 #define LAH_LAUNCH_M(BN, ST)                                                                                   \
     if (!b_mn && !out_f32) return launch<BN, ST, MODE_MGROUP, false, false, false>(p, tmA, tmB, max_ctas, stream); \
     if (b_mn && !out_f32) return launch<BN, ST, MODE_MGROUP, false, true, false>(p, tmA, tmB, max_ctas, stream);   \
@@ -441,6 +451,7 @@ int lah_gemm_kgroup(const void* A, long long lda, const void* B, long long ldb, 
     GemmParams p;
     p.N = N; p.K = 0; p.M = M; p.num_groups = G; p.num_m_tiles = 0; p.tile_group = nullptr; p.group_off = group_off;
     p.C = C; p.ldc = ldc; p.c_group_stride = c_group_stride; p.bias = nullptr; p.residual = nullptr; p.ldr = 0;
+    p.wait_flags = nullptr; p.wait_count = 0; p.wait_epoch = 0; p.status = nullptr;
     if (block_n == 256) return launch<256, 4, MODE_KGROUP, true, true, true>(p, tmA, tmB, max_ctas, stream);
     if (block_n == 128) return launch<128, 6, MODE_KGROUP, true, true, true>(p, tmA, tmB, max_ctas, stream);
     if (block_n == 64) return launch<64, 8, MODE_KGROUP, true, true, true>(p, tmA, tmB, max_ctas, stream);

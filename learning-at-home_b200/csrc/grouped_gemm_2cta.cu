@@ -44,6 +44,9 @@ struct Params {
     const float* bias;
     const bf16* residual;
     long long ldr;
+    const int* wait_flags;   // receive-side fusion (see grouped_gemm.cu)
+    int wait_count, wait_epoch;
+    int* status;
 };
 
 template <int MODE, bool A_MN, bool B_MN, bool OUT_F32>
@@ -118,6 +121,11 @@ gemm2_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const __gr
 
     if (warp == 0 && lane == 0) {
         // =============================================================== TMA producer (both CTAs)
+        if (p.wait_flags) {  // rows pushed by peer GPUs over NVLink must have landed before the first TMA load
+            for (int sidx = 0; sidx < p.wait_count; ++sidx)
+                if (!spin_flag_ge(p.wait_flags + sidx, p.wait_epoch)) atomicOr(p.status, 1);
+            fence_proxy_async_global();
+        }
         int stage = 0;
         uint32_t phase = 0;
         for (int tile = pair_id; tile < total_tiles; tile += num_pairs) {
@@ -358,7 +366,8 @@ extern "C" {
 // 128 rows (entries 2t and 2t+1 agree)
 int lah_gemm_mgroup2(const void* A, long long lda, int a_rows, const void* B, int G, int N, int K, int b_mn, void* C,
                      long long ldc, int out_f32, int m_valid, int num_m_tiles128, const int* tile_group,
-                     const float* bias, const void* residual, long long ldr, int max_ctas, cudaStream_t stream) {
+                     const float* bias, const void* residual, long long ldr, int max_ctas, const int* wait_flags,
+                     int wait_count, int wait_epoch, int* status, cudaStream_t stream) {
     if ((K % 8) || (N % 32) || (lda % 8)) return -2;
     CUtensorMap tmA, tmB;
     {
@@ -385,6 +394,7 @@ int lah_gemm_mgroup2(const void* A, long long lda, int a_rows, const void* B, in
     p.N = N; p.K = K; p.M = m_valid; p.num_groups = G; p.num_m_tiles = (num_m_tiles128 + 1) / 2; p.tile_group = tile_group;
     p.group_off = nullptr; p.C = C; p.ldc = ldc; p.c_group_stride = 0; p.bias = bias;
     p.residual = reinterpret_cast<const bf16*>(residual); p.ldr = ldr;
+    p.wait_flags = wait_flags; p.wait_count = wait_count; p.wait_epoch = wait_epoch; p.status = status;
     if (!b_mn && !out_f32) return launch2<MODE_MGROUP, false, false, false>(p, tmA, tmB, max_ctas, stream);
     if (b_mn && !out_f32) return launch2<MODE_MGROUP, false, true, false>(p, tmA, tmB, max_ctas, stream);
     if (!b_mn && out_f32) return launch2<MODE_MGROUP, false, false, true>(p, tmA, tmB, max_ctas, stream);
@@ -413,6 +423,7 @@ int lah_gemm_kgroup2(const void* A, long long lda, const void* B, long long ldb,
     Params p;
     p.N = N; p.K = 0; p.M = M; p.num_groups = G; p.num_m_tiles = 0; p.tile_group = nullptr; p.group_off = group_off;
     p.C = C; p.ldc = ldc; p.c_group_stride = c_group_stride; p.bias = nullptr; p.residual = nullptr; p.ldr = 0;
+    p.wait_flags = nullptr; p.wait_count = 0; p.wait_epoch = 0; p.status = nullptr;
     return launch2<MODE_KGROUP, true, true, true>(p, tmA, tmB, max_ctas, stream);
 }
 

@@ -416,11 +416,28 @@ struct CombineArgs {
     const float* w;           // [B*k] or nullptr
     bf16* out;                // [B, H]
     int B, k, H, E_loc;
+    // fused flag protocol: block 0 publishes 'my expert outputs are complete' to every peer, every block waits for all
+    long long flags_off;
+    int slot, epoch, do_signal, do_wait;
+    int* status;
 };
 
 template <int VEC_PER_LANE>
 __global__ void __launch_bounds__(256) combine_rows_kernel(Peers peers, CombineArgs a) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (a.do_signal && blockIdx.x == 0 && threadIdx.x < peers.world) {
+        // everything launched before this kernel on the stream (the last expert GEMM) is complete: tell the peers
+        __threadfence_system();
+        int* f = reinterpret_cast<int*>(peers.base[threadIdx.x] + a.flags_off) + a.slot * MAX_WORLD + peers.me;
+        st_release_sys(f, a.epoch);
+    }
+    if (a.do_wait) {
+        if (threadIdx.x < peers.world) {
+            const int* f = reinterpret_cast<const int*>(peers.base[peers.me] + a.flags_off) + a.slot * MAX_WORLD + threadIdx.x;
+            spin_until_ge(f, a.epoch, a.status);
+        }
+        __syncthreads();
+    }
     const int b = blockIdx.x * 8 + warp;
     if (b >= a.B) return;
     float acc[VEC_PER_LANE * 8];
@@ -628,12 +645,14 @@ int lah_signal_wait(long long flags_off, int slot, int epoch, int do_signal, int
 }
 
 int lah_combine_rows(long long src_off, const int* idx, const int* pair_row, const float* w, void* out, int B, int k,
-                     int H, int E_loc, cudaStream_t st) {
+                     int H, int E_loc, long long flags_off, int slot, int epoch, int do_signal, int do_wait, int* status,
+                     cudaStream_t st) {
     if (!g_peers_set) return -10;
     if (B <= 0) return 0;
     CombineArgs a;
     a.src_off = src_off; a.idx = idx; a.pair_row = pair_row; a.w = w; a.out = (bf16*)out; a.B = B; a.k = k; a.H = H;
-    a.E_loc = E_loc;
+    a.E_loc = E_loc; a.flags_off = flags_off; a.slot = slot; a.epoch = epoch; a.do_signal = do_signal; a.do_wait = do_wait;
+    a.status = status;
     const int grid = (B + 7) / 8;
     if (H == 256) combine_rows_kernel<1><<<grid, 256, 0, st>>>(g_peers, a);
     else if (H == 512) combine_rows_kernel<2><<<grid, 256, 0, st>>>(g_peers, a);

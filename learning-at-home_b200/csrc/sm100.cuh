@@ -284,6 +284,17 @@ __device__ __forceinline__ void st_v4(int4* p, const int4& v) {
                  : "memory");
 }
 
+// wait until a flag written by a peer GPU (st.release.sys) reaches `epoch`; returns false after ~10 s (dead peer)
+__device__ __forceinline__ bool spin_flag_ge(const int* flag, int epoch) {
+    const long long t0 = clock64();
+    while (ld_acquire_sys(flag) < epoch) {
+        if (clock64() - t0 > 20000000000ll) return false;
+    }
+    return true;
+}
+// order generic-proxy observations (the acquire above) before subsequent async-proxy (TMA) reads of global memory
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+
 // ----------------------------------------------------------------------------------------------
 // small numeric helpers
 // ----------------------------------------------------------------------------------------------

@@ -27,13 +27,15 @@ def _lib():
     if not _configured:
         lib.lah_gemm_mgroup.restype = c_int
         lib.lah_gemm_mgroup.argtypes = [c_void_p, c_ll, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_ll,
-                                        c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_int, c_void_p]
+                                        c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_int, c_void_p, c_int, c_int,
+                                        c_void_p, c_void_p]
         lib.lah_gemm_kgroup.restype = c_int
         lib.lah_gemm_kgroup.argtypes = [c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p,
                                         c_void_p, c_ll, c_ll, c_int, c_int, c_void_p]
         lib.lah_gemm_mgroup2.restype = c_int
         lib.lah_gemm_mgroup2.argtypes = [c_void_p, c_ll, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_ll,
-                                         c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_void_p]
+                                         c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_void_p, c_int, c_int, c_void_p,
+                                         c_void_p]
         lib.lah_gemm_kgroup2.restype = c_int
         lib.lah_gemm_kgroup2.argtypes = [c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p,
                                          c_void_p, c_ll, c_ll, c_int, c_void_p]
@@ -50,7 +52,7 @@ def _pick_block_n(n: int) -> int:
 
 
 def grouped_linear(a, w, *, tile_group=None, bias=None, residual=None, w_is_kn=False, out=None,
-                   out_dtype=torch.bfloat16, m_valid=None, block_n=None, max_ctas=0, two_cta=False):
+                   out_dtype=torch.bfloat16, m_valid=None, block_n=None, max_ctas=0, two_cta=False, wait=None):
     """
     out[r, :] = a[r, :] @ W[g(r)]^T (+ bias[g(r)]) (+ residual[r, :])
 
@@ -58,7 +60,10 @@ def grouped_linear(a, w, *, tile_group=None, bias=None, residual=None, w_is_kn=F
     :param w: [G, N, K] bf16 (w_is_kn=False, y = x W^T)   or   [G, K, N] bf16 (w_is_kn=True, y = x W: dgrad)
     :param tile_group: int32 [ceil(rows/128)] expert of every 128-row tile (-1 skips the tile); None => expert 0
     :param bias: fp32 [G, N] or None;  residual: bf16 [rows, N] or None
+    :param wait: (flags int32 tensor [count], epoch, status tensor) — receive-side fusion: the kernel's TMA producer
+        polls the peers' dispatch flags (ld.acquire.sys) before its first load instead of a separate wait kernel
     """
+    wait_flags, wait_count, wait_epoch, wait_status = (wait[0], wait[0].numel(), wait[1], wait[2]) if wait else (None, 0, 0, None)
     assert a.is_cuda and a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and a.dim() == 2 and w.dim() == 3
     assert a.stride(1) == 1 and w.is_contiguous()
     rows, K = a.shape
@@ -84,7 +89,8 @@ def grouped_linear(a, w, *, tile_group=None, bias=None, residual=None, w_is_kn=F
         code = _lib().lah_gemm_mgroup2(
             ptr(a), a.stride(0), rows, ptr(w), G, N, K, int(w_is_kn), ptr(out), out.stride(0),
             int(out.dtype == torch.float32), rows if m_valid is None else m_valid, num_m_tiles, ptr(tile_group),
-            ptr(bias), ptr(residual), residual.stride(0) if residual is not None else 0, max_ctas, stream_ptr())
+            ptr(bias), ptr(residual), residual.stride(0) if residual is not None else 0, max_ctas, ptr(wait_flags),
+            wait_count, wait_epoch, ptr(wait_status), stream_ptr())
         native.check(code, "lah_gemm_mgroup2")
         native.count_launch()
         return out
@@ -92,7 +98,8 @@ def grouped_linear(a, w, *, tile_group=None, bias=None, residual=None, w_is_kn=F
     code = _lib().lah_gemm_mgroup(
         ptr(a), a.stride(0), rows, ptr(w), G, N, K, int(w_is_kn), ptr(out), out.stride(0),
         int(out.dtype == torch.float32), rows if m_valid is None else m_valid, num_m_tiles, ptr(tile_group),
-        ptr(bias), ptr(residual), residual.stride(0) if residual is not None else 0, bn, max_ctas, stream_ptr())
+        ptr(bias), ptr(residual), residual.stride(0) if residual is not None else 0, bn, max_ctas, ptr(wait_flags),
+        wait_count, wait_epoch, ptr(wait_status), stream_ptr())
     native.check(code, "lah_gemm_mgroup")
     native.count_launch()
     return out

@@ -34,7 +34,7 @@ def _lib():
         "lah_layout_exchange": [L, L, I, I, I, I, I, I, P, P, P, P, P, P, P, P],
         "lah_scatter_rows": [P, P, P, P, P, P, L, L, I, I, I, I, I, I, I, I, P, P, P, P, P],
         "lah_signal_wait": [L, I, I, I, I, P, P],
-        "lah_combine_rows": [L, P, P, P, P, I, I, I, I, P],
+        "lah_combine_rows": [L, P, P, P, P, I, I, I, I, L, I, I, I, I, P, P],
         "lah_gate_bwd": [L, P, P, P, P, P, I, I, I, I, P, I, P],
         "lah_adam_step": [P, P, P, P, P, P, I, P, I, P, P, I, Fl, Fl, Fl, Fl, Fl, I, I, I, L, P, Fl, P],
         "lah_bump_steps": [P, P, I, P],
@@ -131,10 +131,14 @@ def signal_wait(flags_off, slot, epoch, status, *, signal=True, wait=True):
     native.count_launch()
 
 
-def combine_rows(src_off, idx, pair_row, w, out, k, E_loc):
+def combine_rows(src_off, idx, pair_row, w, out, k, E_loc, *, flags_off=0, slot=0, epoch=0, signal=False, wait=False,
+                 status=None):
+    """weighted P2P gather; with signal/wait the kernel itself publishes 'my expert outputs are ready' to every peer
+    and waits for all peers' flags before pulling their rows (no separate flag kernels)"""
     B, H = out.shape
-    native.check(_lib().lah_combine_rows(src_off, ptr(idx), ptr(pair_row), ptr(w), ptr(out), B, k, H, E_loc,
-                                         stream_ptr()), "lah_combine_rows")
+    native.check(_lib().lah_combine_rows(src_off, ptr(idx), ptr(pair_row), ptr(w), ptr(out), B, k, H, E_loc, flags_off,
+                                         slot, epoch, int(signal), int(wait), ptr(status), stream_ptr()),
+                 "lah_combine_rows")
     native.count_launch()
     return out
 

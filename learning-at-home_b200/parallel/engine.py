@@ -357,20 +357,20 @@ class FusedDMoE(nn.Module):
                           tile_group=ws.tile_group, total_rows=ws.total_rows, status=c.status)
         K.scatter_rows(x, None, idx, pos, ws.dst_row, pair_row, ws.xd_off, c.flags_off, K.SLOT_DISPATCH, epoch, k,
                        c.E_loc, c.max_rows, ws.group_off, ws.group_rows, c.done_counter, c.status, align=c.align)
-        if c.world > 1:
-            K.signal_wait(c.flags_off, K.SLOT_DISPATCH, epoch, c.status, signal=False, wait=True)
-        # ---- expert FFN on the rows this rank received (grouped by expert)
+        # ---- expert FFN on the rows this rank received (grouped by expert).  Receive-side fusion: the first GEMM's TMA
+        # producer polls the peers' dispatch flags itself (no separate wait kernel)
         tg = ws.tile_group
-        gemm.grouped_linear(ws.xd, sh.bf16["w1"], tile_group=tg, bias=sh.views["b1"], out=ws.h1, two_cta=c.two_cta)
+        wait = (c.flags[K.SLOT_DISPATCH, :c.world], epoch, c.status) if c.world > 1 else None
+        gemm.grouped_linear(ws.xd, sh.bf16["w1"], tile_group=tg, bias=sh.views["b1"], out=ws.h1, two_cta=c.two_cta,
+                            wait=wait)
         K.ln_relu_fwd(ws.h1, sh.views["g1"], sh.views["be1"], tg, out=ws.a1, mean=ws.mean1, rstd=ws.rstd1)
         gemm.grouped_linear(ws.a1, sh.bf16["w2"], tile_group=tg, bias=sh.views["b2"], out=ws.h2, two_cta=c.two_cta)
         K.ln_relu_fwd(ws.h2, sh.views["g2"], sh.views["be2"], tg, out=ws.a2, mean=ws.mean2, rstd=ws.rstd2)
         gemm.grouped_linear(ws.a2, sh.bf16["w3"], tile_group=tg, bias=sh.views["b3"], residual=ws.xd, out=ws.yo,
                             two_cta=c.two_cta)
-        if c.world > 1:
-            K.signal_wait(c.flags_off, K.SLOT_OUTPUT, epoch, c.status, signal=True, wait=True)
         y = torch.empty(B, cfg.hidden, dtype=torch.bfloat16, device=x.device)
-        K.combine_rows(ws.yo_off, idx, pair_row, w, y, k, c.E_loc)
+        K.combine_rows(ws.yo_off, idx, pair_row, w, y, k, c.E_loc, flags_off=c.flags_off, slot=K.SLOT_OUTPUT, epoch=epoch,
+                       signal=c.world > 1, wait=c.world > 1, status=c.status)
         return y
 
     def _backward_cuda(self, gy, B):
@@ -384,7 +384,7 @@ class FusedDMoE(nn.Module):
         K.gate_bwd(ws.yo_off, gy, idx, pair_row, w, dlogits, k, c.E_loc, self.grid_size)
         K.scatter_rows(gy, w, idx, pos, None, pair_row, c.gyd_off, c.flags_off, K.SLOT_GRAD, epoch, k, c.E_loc,
                        c.max_rows, ws.group_off, ws.group_rows, c.done_counter, c.status, align=c.align)
-        if c.world > 1:
+        if c.world > 1:  # the first consumers of the pushed gradients are the colsum / wgrad kernels
             K.signal_wait(c.flags_off, K.SLOT_GRAD, epoch, c.status, signal=False, wait=True)
         tg, go, G = ws.tile_group, ws.group_off, c.E_loc
         gr = sh.grads
@@ -402,10 +402,9 @@ class FusedDMoE(nn.Module):
                             two_cta=c.two_cta)
         # ---- expert-side optimizer step (reference: ExpertBackend.apply_gradients right after backward)
         self.apply_expert_gradients()
-        if c.world > 1:
-            K.signal_wait(c.flags_off, K.SLOT_DINPUT, epoch, c.status, signal=True, wait=True)
         dx = torch.empty(B, cfg.hidden, dtype=torch.bfloat16, device=gy.device)
-        K.combine_rows(c.dxd_off, idx, pair_row, None, dx, k, c.E_loc)
+        K.combine_rows(c.dxd_off, idx, pair_row, None, dx, k, c.E_loc, flags_off=c.flags_off, slot=K.SLOT_DINPUT,
+                       epoch=epoch, signal=c.world > 1, wait=c.world > 1, status=c.status)
         return dx, dlogits
 
     def apply_expert_gradients(self):
