@@ -32,7 +32,10 @@ constexpr int MODE_KGROUP = 1;
 constexpr int A_BYTES = CTA_M * BLOCK_K * 2;   // 16 KB
 constexpr int B_BYTES = CTA_N * BLOCK_K * 2;   // 16 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+constexpr int EPI_ROW_BYTES = 144;                       // 128 B of payload + 16 B pad: conflict-free 16 B accesses
+constexpr int EPI_WARP_BYTES = 32 * EPI_ROW_BYTES;       // one 32-row staging slab per epilogue warp
+constexpr int EPI_OFFSET = STAGES * STAGE_BYTES;
+constexpr int BAR_OFFSET = EPI_OFFSET + 4 * EPI_WARP_BYTES;
 constexpr int SMEM_TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 1024;
 
 struct Params {
@@ -217,64 +220,86 @@ gemm2_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const __gr
             const uint32_t aphase = (iter >> 1) & 1;
             mbar_wait(&tmem_full[as], aphase);
             tcgen05_fence_after();
-            const int row = m_row + cta_rank * CTA_M + lane_group * 32 + lane;
-            const bool row_ok = (MODE == MODE_KGROUP) ? true : (row < p.M);
+            // Each thread owns one accumulator row (tcgen05.ld 32x32b).  Storing rows straight from registers makes every
+            // warp-level 16 B store touch 32 different 128 B lines (32 L1 wavefronts / instruction; the epilogue was the
+            // bottleneck of the K = 512 GEMMs: 38 % tensor-pipe activity in ncu).  So the warp transposes through a
+            // padded smem slab and writes 4 full 128 B lines per instruction instead.
+            const int row_base = m_row + cta_rank * CTA_M + lane_group * 32;   // first row of this warp's slab
+            const int row = row_base + lane;
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_group * 32) << 16) + as * TILE_N;
+            uint8_t* slab = smem + EPI_OFFSET + (warp - 2) * EPI_WARP_BYTES;
+            constexpr int COLS_PER_ITER = OUT_F32 ? 32 : 64;   // 128 B of output per row per iteration
 #pragma unroll 1
-            for (int c = 0; c < TILE_N / 32; ++c) {
-                uint32_t r[32];
-                tmem_ld_32x32(taddr + c * 32, r);
-                tmem_ld_wait();
-                const int col = n_col + c * 32;
-                if (col >= p.N || !row_ok) continue;
-                float v[32];
+            for (int c0 = 0; c0 < TILE_N; c0 += COLS_PER_ITER) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                if (MODE == MODE_MGROUP) {
-                    if (p.bias) {
-                        const float4* bp = reinterpret_cast<const float4*>(p.bias + static_cast<long long>(g) * p.N + col);
+                for (int hf = 0; hf < COLS_PER_ITER / 32; ++hf) {
+                    uint32_t r[32];
+                    tmem_ld_32x32(taddr + c0 + hf * 32, r);
+                    tmem_ld_wait();
+                    const int col = n_col + c0 + hf * 32;
+                    float v[32];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const float4 b = __ldg(bp + j);
-                            v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                    if (MODE == MODE_MGROUP) {
+                        if (p.bias) {
+                            const float4* bp = reinterpret_cast<const float4*>(p.bias + static_cast<long long>(g) * p.N + col);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const float4 b = __ldg(bp + j);
+                                v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+                            }
                         }
-                    }
-                    if (p.residual) {
-                        const int4* rp = reinterpret_cast<const int4*>(p.residual + static_cast<long long>(row) * p.ldr + col);
+                        if (p.residual && row < p.M) {
+                            const int4* rp = reinterpret_cast<const int4*>(p.residual + static_cast<long long>(row) * p.ldr + col);
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const int4 q = __ldg(rp + j);
-                            const uint32_t w[4] = {(uint32_t)q.x, (uint32_t)q.y, (uint32_t)q.z, (uint32_t)q.w};
+                            for (int j = 0; j < 4; ++j) {
+                                const int4 q = __ldg(rp + j);
+                                const uint32_t w[4] = {(uint32_t)q.x, (uint32_t)q.y, (uint32_t)q.z, (uint32_t)q.w};
 #pragma unroll
-                            for (int t = 0; t < 4; ++t) {
-                                const float2 f = unpack_bf16x2(w[t]);
-                                v[8 * j + 2 * t] += f.x;
-                                v[8 * j + 2 * t + 1] += f.y;
+                                for (int t = 0; t < 4; ++t) {
+                                    const float2 f = unpack_bf16x2(w[t]);
+                                    v[8 * j + 2 * t] += f.x;
+                                    v[8 * j + 2 * t + 1] += f.y;
+                                }
                             }
                         }
                     }
-                }
-                if (OUT_F32) {
-                    float* cp = reinterpret_cast<float*>(p.C) +
-                                (MODE == MODE_KGROUP ? static_cast<long long>(g) * p.c_group_stride : 0ll) +
-                                static_cast<long long>(row) * p.ldc + col;
+                    uint8_t* my = slab + lane * EPI_ROW_BYTES;
+                    if (OUT_F32) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        *reinterpret_cast<float4*>(cp + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                } else {
-                    bf16* cp = reinterpret_cast<bf16*>(p.C) +
-                               (MODE == MODE_KGROUP ? static_cast<long long>(g) * p.c_group_stride : 0ll) +
-                               static_cast<long long>(row) * p.ldc + col;
+                        for (int j = 0; j < 8; ++j)
+                            *reinterpret_cast<float4*>(my + 16 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    } else {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        int4 q;
-                        q.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
-                        q.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-                        q.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
-                        q.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
-                        *reinterpret_cast<int4*>(cp + 8 * j) = q;
+                        for (int j = 0; j < 4; ++j) {
+                            int4 q;
+                            q.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+                            q.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+                            q.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+                            q.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+                            *reinterpret_cast<int4*>(my + hf * 64 + 16 * j) = q;
+                        }
                     }
                 }
+                __syncwarp();
+                // coalesced write-out: 8 lanes cover one 128 B row segment, 4 rows per instruction
+                const int chunk = lane & 7;
+                uint8_t* cbase = reinterpret_cast<uint8_t*>(p.C) +
+                                 ((MODE == MODE_KGROUP ? static_cast<long long>(g) * p.c_group_stride : 0ll) + n_col + c0) *
+                                     (OUT_F32 ? 4 : 2) +
+                                 chunk * 16;
+                const long long row_bytes = p.ldc * (OUT_F32 ? 4 : 2);
+                if (n_col + c0 < p.N) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int rl = i * 4 + (lane >> 3);
+                        const int grow = row_base + rl;
+                        const int4 q = *reinterpret_cast<const int4*>(slab + rl * EPI_ROW_BYTES + chunk * 16);
+                        if (MODE == MODE_KGROUP || grow < p.M)
+                            *reinterpret_cast<int4*>(cbase + static_cast<long long>(grow) * row_bytes) = q;
+                    }
+                }
+                __syncwarp();
             }
             tcgen05_fence_before();
             __syncwarp();

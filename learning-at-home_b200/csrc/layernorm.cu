@@ -16,11 +16,10 @@ constexpr float LN_EPS = 1e-5f;
 //   a = relu((h - mean) * rstd * gamma + beta);  saves mean / rstd per row
 // ------------------------------------------------------------------------------------------------
 template <int C>
-__global__ void __launch_bounds__(256) ln_relu_fwd_kernel(const bf16* __restrict__ h, bf16* __restrict__ a,
-                                                          float* __restrict__ mean_out, float* __restrict__ rstd_out,
-                                                          const float* __restrict__ gamma,
-                                                          const float* __restrict__ beta,
-                                                          const int* __restrict__ tile_group, int rows, int relu) {
+__global__ void __launch_bounds__(256, (C <= 2048) ? 3 : 1) ln_relu_fwd_kernel(
+    const bf16* __restrict__ h, bf16* __restrict__ a, float* __restrict__ mean_out, float* __restrict__ rstd_out,
+    const float* __restrict__ gamma, const float* __restrict__ beta, const int* __restrict__ tile_group, int rows,
+    int relu) {
     constexpr int NV = C / 256;  // int4 (8 x bf16) chunks per lane
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row = blockIdx.x * 8 + warp;
@@ -28,26 +27,32 @@ __global__ void __launch_bounds__(256) ln_relu_fwd_kernel(const bf16* __restrict
     const int g = tile_group ? __ldg(tile_group + (row >> 7)) : 0;
     if (g < 0) return;
     const int4* hp = reinterpret_cast<const int4*>(h + static_cast<long long>(row) * C);
-    float v[NV * 8];
+    // the row stays PACKED (bf16x2) in registers: 4 regs per 8 values instead of 8 -> more resident warps, i.e. more
+    // bytes in flight per SM for this purely bandwidth-bound kernel; values are unpacked on the fly in each pass
+    int4 q[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) q[j] = ld_nc_v4(hp + j * 32 + lane);
     float s = 0.f;
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
-        const int4 q = ld_nc_v4(hp + j * 32 + lane);
-        const uint32_t w[4] = {(uint32_t)q.x, (uint32_t)q.y, (uint32_t)q.z, (uint32_t)q.w};
+        const uint32_t w[4] = {(uint32_t)q[j].x, (uint32_t)q[j].y, (uint32_t)q[j].z, (uint32_t)q[j].w};
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
             const float2 f = unpack_bf16x2(w[t]);
-            v[j * 8 + 2 * t] = f.x;
-            v[j * 8 + 2 * t + 1] = f.y;
             s += f.x + f.y;
         }
     }
     const float mean = warp_sum(s) * (1.f / C);
     float ss = 0.f;
 #pragma unroll
-    for (int i = 0; i < NV * 8; ++i) {
-        const float d = v[i] - mean;
-        ss += d * d;
+    for (int j = 0; j < NV; ++j) {
+        const uint32_t w[4] = {(uint32_t)q[j].x, (uint32_t)q[j].y, (uint32_t)q[j].z, (uint32_t)q[j].w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const float2 f = unpack_bf16x2(w[t]);
+            const float d0 = f.x - mean, d1 = f.y - mean;
+            ss += d0 * d0 + d1 * d1;
+        }
     }
     const float rstd = rsqrtf(warp_sum(ss) * (1.f / C) + LN_EPS);
     if (lane == 0) {
@@ -66,18 +71,24 @@ __global__ void __launch_bounds__(256) ln_relu_fwd_kernel(const bf16* __restrict
         const float4 b1 = __ldg(reinterpret_cast<const float4*>(bp + col + 4));
         const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
         const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        const uint32_t w[4] = {(uint32_t)q[j].x, (uint32_t)q[j].y, (uint32_t)q[j].z, (uint32_t)q[j].w};
         float y[8];
 #pragma unroll
-        for (int t = 0; t < 8; ++t) {
-            y[t] = (v[j * 8 + t] - mean) * rstd * gg[t] + bb[t];
-            if (relu) y[t] = fmaxf(y[t], 0.f);
+        for (int t = 0; t < 4; ++t) {
+            const float2 f = unpack_bf16x2(w[t]);
+            y[2 * t] = (f.x - mean) * rstd * gg[2 * t] + bb[2 * t];
+            y[2 * t + 1] = (f.y - mean) * rstd * gg[2 * t + 1] + bb[2 * t + 1];
         }
-        int4 q;
-        q.x = pack_bf16x2(y[0], y[1]);
-        q.y = pack_bf16x2(y[2], y[3]);
-        q.z = pack_bf16x2(y[4], y[5]);
-        q.w = pack_bf16x2(y[6], y[7]);
-        ap[j * 32 + lane] = q;
+        if (relu) {
+#pragma unroll
+            for (int t = 0; t < 8; ++t) y[t] = fmaxf(y[t], 0.f);
+        }
+        int4 o;
+        o.x = pack_bf16x2(y[0], y[1]);
+        o.y = pack_bf16x2(y[2], y[3]);
+        o.z = pack_bf16x2(y[4], y[5]);
+        o.w = pack_bf16x2(y[6], y[7]);
+        ap[j * 32 + lane] = o;
     }
 }
 

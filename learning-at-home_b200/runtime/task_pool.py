@@ -83,6 +83,7 @@ class TaskPool(TaskPoolBase):
         self._pending: Dict[int, List[Task]] = {}
         self._next_batch_index = 0
         self._staging: Dict[Tuple[int, int], torch.Tensor] = {}
+        self._staging_free = None  # CUDA event: H2D copies out of the staging buffers have completed
         self._alive = False
         self.on_task = None  # set by the runtime: wakes its scheduler when a task arrives
         if start:
@@ -171,17 +172,25 @@ class TaskPool(TaskPoolBase):
         to_cuda = device is not None and torch.device(device).type == "cuda"
         batch = []
         from ..ops import host
+        if to_cuda and self._staging_free is not None:
+            self._staging_free.synchronize()  # the previous batch's H2D copies have left the pinned staging buffers
         for i, proto in enumerate(self.inputs_schema):
             parts = [task.args[i] for task in tasks]
-            if len(parts) == 1 and not to_cuda:
-                tensor = parts[0]
-            else:
-                staged = self._staging_buffer(i, rows, proto, parts[0], pin=to_cuda)
+            if to_cuda:
+                # assemble into a reusable PINNED buffer (native threaded gather), then one async H2D copy
+                staged = self._staging_buffer(i, rows, proto, parts[0], pin=True)
                 host.gather_rows(parts, staged)
-                tensor = staged
-            if device is not None:
-                tensor = tensor.to(device, non_blocking=True)
+                tensor = staged.to(device, non_blocking=True)
+            else:
+                # host execution: the batch must own its memory (the runtime may still hold the previous batch)
+                tensor = parts[0] if len(parts) == 1 else host.gather_rows(
+                    parts, torch.empty((rows, *parts[0].shape[1:]), dtype=parts[0].dtype))
+                if device is not None:
+                    tensor = tensor.to(device)
             batch.append(tensor)
+        if to_cuda:
+            self._staging_free = torch.cuda.Event()
+            self._staging_free.record(torch.cuda.current_stream(device))
         return batch_index, batch
 
     def send_outputs_from_runtime(self, batch_index: int, batch_outputs: Sequence):
