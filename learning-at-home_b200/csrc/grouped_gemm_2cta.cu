@@ -50,6 +50,7 @@ struct Params {
     const int* wait_flags;   // receive-side fusion (see grouped_gemm.cu)
     int wait_count, wait_epoch;
     int* status;
+    int act;                 // epilogue activation after the bias: 0 none, 1 ReLU, 2 GELU (erf)
 };
 
 template <int MODE, bool A_MN, bool B_MN, bool OUT_F32>
@@ -249,6 +250,13 @@ gemm2_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const __gr
                                 v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
                             }
                         }
+                        if (p.act == 1) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+                        } else if (p.act == 2) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = 0.5f * v[j] * (1.f + erff(v[j] * 0.70710678118654752f));
+                        }
                         if (p.residual && row < p.M) {
                             const int4* rp = reinterpret_cast<const int4*>(p.residual + static_cast<long long>(row) * p.ldr + col);
 #pragma unroll
@@ -392,7 +400,7 @@ extern "C" {
 int lah_gemm_mgroup2(const void* A, long long lda, int a_rows, const void* B, int G, int N, int K, int b_mn, void* C,
                      long long ldc, int out_f32, int m_valid, int num_m_tiles128, const int* tile_group,
                      const float* bias, const void* residual, long long ldr, int max_ctas, const int* wait_flags,
-                     int wait_count, int wait_epoch, int* status, cudaStream_t stream) {
+                     int wait_count, int wait_epoch, int* status, int act, cudaStream_t stream) {
     if ((K % 8) || (N % 32) || (lda % 8)) return -2;
     CUtensorMap tmA, tmB;
     {
@@ -419,7 +427,7 @@ int lah_gemm_mgroup2(const void* A, long long lda, int a_rows, const void* B, in
     p.N = N; p.K = K; p.M = m_valid; p.num_groups = G; p.num_m_tiles = (num_m_tiles128 + 1) / 2; p.tile_group = tile_group;
     p.group_off = nullptr; p.C = C; p.ldc = ldc; p.c_group_stride = 0; p.bias = bias;
     p.residual = reinterpret_cast<const bf16*>(residual); p.ldr = ldr;
-    p.wait_flags = wait_flags; p.wait_count = wait_count; p.wait_epoch = wait_epoch; p.status = status;
+    p.wait_flags = wait_flags; p.wait_count = wait_count; p.wait_epoch = wait_epoch; p.status = status; p.act = act;
     if (!b_mn && !out_f32) return launch2<MODE_MGROUP, false, false, false>(p, tmA, tmB, max_ctas, stream);
     if (b_mn && !out_f32) return launch2<MODE_MGROUP, false, true, false>(p, tmA, tmB, max_ctas, stream);
     if (!b_mn && out_f32) return launch2<MODE_MGROUP, false, false, true>(p, tmA, tmB, max_ctas, stream);
@@ -448,7 +456,7 @@ int lah_gemm_kgroup2(const void* A, long long lda, const void* B, long long ldb,
     Params p;
     p.N = N; p.K = 0; p.M = M; p.num_groups = G; p.num_m_tiles = 0; p.tile_group = nullptr; p.group_off = group_off;
     p.C = C; p.ldc = ldc; p.c_group_stride = c_group_stride; p.bias = nullptr; p.residual = nullptr; p.ldr = 0;
-    p.wait_flags = nullptr; p.wait_count = 0; p.wait_epoch = 0; p.status = nullptr;
+    p.wait_flags = nullptr; p.wait_count = 0; p.wait_epoch = 0; p.status = nullptr; p.act = 0;
     return launch2<MODE_KGROUP, true, true, true>(p, tmA, tmB, max_ctas, stream);
 }
 

@@ -35,7 +35,7 @@ def _lib():
         lib.lah_gemm_mgroup2.restype = c_int
         lib.lah_gemm_mgroup2.argtypes = [c_void_p, c_ll, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_ll,
                                          c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_void_p, c_int, c_int, c_void_p,
-                                         c_void_p]
+                                         c_int, c_void_p]
         lib.lah_gemm_kgroup2.restype = c_int
         lib.lah_gemm_kgroup2.argtypes = [c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p,
                                          c_void_p, c_ll, c_ll, c_int, c_void_p]
@@ -52,7 +52,7 @@ def _pick_block_n(n: int) -> int:
 
 
 def grouped_linear(a, w, *, tile_group=None, bias=None, residual=None, w_is_kn=False, out=None,
-                   out_dtype=torch.bfloat16, m_valid=None, block_n=None, max_ctas=0, two_cta=False, wait=None):
+                   out_dtype=torch.bfloat16, m_valid=None, block_n=None, max_ctas=0, two_cta=False, wait=None, act=0):
     """
     out[r, :] = a[r, :] @ W[g(r)]^T (+ bias[g(r)]) (+ residual[r, :])
 
@@ -60,6 +60,7 @@ def grouped_linear(a, w, *, tile_group=None, bias=None, residual=None, w_is_kn=F
     :param w: [G, N, K] bf16 (w_is_kn=False, y = x W^T)   or   [G, K, N] bf16 (w_is_kn=True, y = x W: dgrad)
     :param tile_group: int32 [ceil(rows/128)] expert of every 128-row tile (-1 skips the tile); None => expert 0
     :param bias: fp32 [G, N] or None;  residual: bf16 [rows, N] or None
+    :param act: activation fused after the bias (CTA-pair kernel only): 0 none, 1 ReLU, 2 GELU(erf)
     :param wait: (flags int32 tensor [count], epoch, status tensor) — receive-side fusion: the kernel's TMA producer
         polls the peers' dispatch flags (ld.acquire.sys) before its first load instead of a separate wait kernel
     """
@@ -90,10 +91,11 @@ def grouped_linear(a, w, *, tile_group=None, bias=None, residual=None, w_is_kn=F
             ptr(a), a.stride(0), rows, ptr(w), G, N, K, int(w_is_kn), ptr(out), out.stride(0),
             int(out.dtype == torch.float32), rows if m_valid is None else m_valid, num_m_tiles, ptr(tile_group),
             ptr(bias), ptr(residual), residual.stride(0) if residual is not None else 0, max_ctas, ptr(wait_flags),
-            wait_count, wait_epoch, ptr(wait_status), stream_ptr())
+            wait_count, wait_epoch, ptr(wait_status), int(act), stream_ptr())
         native.check(code, "lah_gemm_mgroup2")
         native.count_launch()
         return out
+    assert act == 0, "epilogue activations are implemented in the CTA-pair kernel (two_cta=True, N % 256 == 0)"
     bn = block_n or _pick_block_n(N)
     code = _lib().lah_gemm_mgroup(
         ptr(a), a.stride(0), rows, ptr(w), G, N, K, int(w_is_kn), ptr(out), out.stride(0),

@@ -39,6 +39,7 @@ def _lib():
         "lah_adam_step": [P, P, P, P, P, P, I, P, I, P, P, I, Fl, Fl, Fl, Fl, Fl, I, I, I, L, P, Fl, P],
         "lah_bump_steps": [P, P, I, P],
         "lah_cast_bf16": [P, P, L, P],
+        "lah_attention_fwd": [P, P, I, I, I, P],
         "lah_symm_alloc": [c_ull, ctypes.POINTER(c_void_p)],
         "lah_symm_free": [P],
         "lah_symm_get_handle": [P, ctypes.c_char_p],
@@ -151,6 +152,36 @@ def gate_bwd(yo_off, grad, idx, pair_row, w, dlogits, k, E_loc, grid_size):
                  "lah_gate_bwd")
     native.count_launch()
     return dlogits
+
+
+# ---------------------------------------------------------------------------------------------------------
+# attention (transformer expert)
+# ---------------------------------------------------------------------------------------------------------
+def attention_fwd(qkv, num_heads, *, out=None):
+    """
+    Self-attention over 512-token sequences on tcgen05 (csrc/attention.cu).
+    :param qkv: [batch*512, 3*d_model] bf16 = in_proj output, [q | k | v] per token; head_dim must be 64
+    :returns: [batch*512, d_model] bf16, heads concatenated (input of out_proj)
+    """
+    tokens, three_d = qkv.shape
+    d_model = three_d // 3
+    assert qkv.is_cuda and qkv.dtype == torch.bfloat16 and qkv.is_contiguous() and tokens % 512 == 0
+    if out is None:
+        out = torch.empty(tokens, d_model, dtype=torch.bfloat16, device=qkv.device)
+    native.check(_lib().lah_attention_fwd(ptr(qkv), ptr(out), tokens // 512, num_heads, d_model, stream_ptr()),
+                 "lah_attention_fwd")
+    native.count_launch()
+    return out
+
+
+def attention_ref(qkv, num_heads, seq_len=512):
+    """fp32 oracle: softmax(q k^T / sqrt(d)) v per head"""
+    tokens, three_d = qkv.shape
+    d = three_d // 3
+    q, k, v = qkv.float().view(tokens // seq_len, seq_len, 3, num_heads, d // num_heads).unbind(2)
+    q, k, v = (t.transpose(1, 2) for t in (q, k, v))  # [B, H, S, hd]
+    att = torch.softmax(q @ k.transpose(-1, -2) / (d // num_heads) ** 0.5, dim=-1) @ v
+    return att.transpose(1, 2).reshape(tokens, d)
 
 
 # ---------------------------------------------------------------------------------------------------------

@@ -1,0 +1,88 @@
+"""GPU check: tcgen05 attention kernel and the native transformer layer vs PyTorch oracles (run via gpurun)."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+import lah_b200  # noqa
+from lah_b200.models.layers import TransformerEncoderLayer
+from lah_b200.models.transformer_native import NativeTransformerLayer
+from lah_b200.ops import kernels as K
+
+results = {}
+
+
+def rel(a, b):
+    return ((a.float() - b.float()).norm() / (b.float().norm() + 1e-12)).item()
+
+
+def timeit(fn, iters=10, warmup=2):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(iters):
+        fn()
+    e.record()
+    torch.cuda.synchronize()
+    return s.elapsed_time(e) / iters
+
+
+def check_attention():
+    torch.manual_seed(0)
+    for batch, heads in [(1, 2), (3, 16)]:
+        d = heads * 64
+        qkv = (torch.randn(batch * 512, 3 * d, device="cuda") * 1.5).to(torch.bfloat16)
+        out = K.attention_fwd(qkv, heads)
+        torch.cuda.synchronize()
+        ref = K.attention_ref(qkv, heads)
+        err = rel(out, ref)
+        results[f"attention_b{batch}_h{heads}"] = dict(ok=err < 2e-2, err=err)
+        print(f"attention_b{batch}_h{heads}", results[f"attention_b{batch}_h{heads}"], flush=True)
+    batch, heads, d = 32, 16, 1024
+    qkv = torch.randn(batch * 512, 3 * d, device="cuda").to(torch.bfloat16)
+    out = torch.empty(batch * 512, d, device="cuda", dtype=torch.bfloat16)
+    ms = timeit(lambda: K.attention_fwd(qkv, heads, out=out))
+    flops = 4.0 * batch * heads * 512 * 512 * 64
+    q4 = qkv.view(batch, 512, 3, heads, 64)
+    q, k, v = (q4[:, :, i].transpose(1, 2) for i in range(3))
+    ms_sdpa = timeit(lambda: torch.nn.functional.scaled_dot_product_attention(q, k, v))
+    results["attention_perf"] = dict(ok=True, ms=ms, tflops=flops / ms / 1e9, sdpa_ms=ms_sdpa, sdpa_tflops=flops / ms_sdpa / 1e9)
+    print("attention_perf", results["attention_perf"], flush=True)
+
+
+def check_layer():
+    torch.manual_seed(1)
+    layer = TransformerEncoderLayer(1024, 16).cuda().eval()
+    native = NativeTransformerLayer(layer)
+    x = torch.randn(4, 512, 1024, device="cuda")
+    with torch.no_grad():
+        ref = layer(x)
+    out = native(x)
+    torch.cuda.synchronize()
+    err = rel(out, ref)
+    results["transformer_layer"] = dict(ok=err < 3e-2, err=err)
+    print("transformer_layer", results["transformer_layer"], flush=True)
+    xb = torch.randn(32, 512, 1024, device="cuda").to(torch.bfloat16)
+    ms = timeit(lambda: native(xb))
+    layer_bf16 = layer.to(torch.bfloat16)
+    with torch.no_grad():
+        ms_torch = timeit(lambda: layer_bf16(xb))
+    tokens = 32 * 512
+    flops = tokens * (2.0 * 8_399_872 - 2 * 4 * 1024) + 4.0 * 32 * 16 * 512 * 512 * 64
+    results["transformer_perf"] = dict(ok=True, ms=ms, tflops=flops / ms / 1e9, torch_bf16_ms=ms_torch,
+                                       seqs_per_s=32 / ms * 1e3, torch_seqs_per_s=32 / ms_torch * 1e3)
+    print("transformer_perf", results["transformer_perf"], flush=True)
+
+
+if __name__ == "__main__":
+    for fn in (check_attention, check_layer):
+        try:
+            fn()
+        except Exception as e:  # noqa
+            import traceback
+            traceback.print_exc()
+            results[fn.__name__] = dict(ok=False, error=repr(e))
+    print("ALL_OK" if all(v.get("ok") for v in results.values()) else "SOME_FAILED")
