@@ -255,7 +255,7 @@ def _measure_ours(args, rank, world, local_rank, B, capacity_factor):
 
     routing = []
     for block in trainer.model.blocks:  # tokens-per-expert histogram of the last step (observability)
-        rows = block.ws.group_rows.float()
+        rows = block.ws.step_rows.float()
         routing.append({"active_experts": int((rows > 0).sum()), "max_rows": int(rows.max()), "mean_rows": float(rows.mean()),
                         "padded_rows": int(block.ws.total_rows.item())})
     if rank == 0:

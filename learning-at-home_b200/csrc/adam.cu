@@ -26,6 +26,11 @@ struct AdamArgs {
     int amsgrad, zero_mask;   // zero_mask bit s => zero the gradient of segment s after use
     // peer reduce
     int world; long long peer_grad_off; char* peer_base[8]; float grad_scale;
+    // experts: only the first G_active slots of every segment are owned (the rest are shadow replicas of other ranks'
+    // experts).  shadow_of[2g] >= 0: expert g was SHADOWED this step -> its weight gradient is the sum of the partial
+    // gradients that the ranks in mask shadow_of[2g+1] left in shadow slot shadow_of[2g] of their (symmetric) gradient
+    // buffers (+ my own partial in the owned slot when my bit is set): the data-parallel reduce is fused into the update
+    int G_active; const int* shadow_of; long long shadow_g_off; int me;
 };
 
 __global__ void __launch_bounds__(256) adam_kernel(AdamArgs a) {
@@ -36,6 +41,7 @@ __global__ void __launch_bounds__(256) adam_kernel(AdamArgs a) {
         for (int t = 1; t < 12; ++t)
             if (t < a.num_segs && i >= a.seg_start[t]) sg = t;
         const int g = static_cast<int>((i - a.seg_start[sg]) / a.seg_n[sg]);
+        if (g >= a.G_active) continue;
         if (a.group_rows && a.group_rows[g] <= 0) continue;
         const int step = a.step ? a.step[g] : a.step_scalar;
         const float bc1 = 1.f - powf(a.beta1, static_cast<float>(step));
@@ -51,6 +57,16 @@ __global__ void __launch_bounds__(256) adam_kernel(AdamArgs a) {
                 gr.x += t.x; gr.y += t.y; gr.z += t.z; gr.w += t.w;
             }
             gr.x *= a.grad_scale; gr.y *= a.grad_scale; gr.z *= a.grad_scale; gr.w *= a.grad_scale;
+        } else if (a.shadow_of && a.shadow_of[2 * g] >= 0) {
+            const int slot = a.shadow_of[2 * g], mask = a.shadow_of[2 * g + 1];
+            gr = ((mask >> a.me) & 1) ? *reinterpret_cast<const float4*>(a.g + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const long long pi = i + (a.G_active + slot - g) * a.seg_n[sg];
+            for (int r = 0; r < a.world; ++r) {
+                if (r == a.me || !((mask >> r) & 1)) continue;
+                const float4 t = *reinterpret_cast<const float4*>(
+                    reinterpret_cast<const float*>(a.peer_base[r] + a.shadow_g_off) + pi);
+                gr.x += t.x; gr.y += t.y; gr.z += t.z; gr.w += t.w;
+            }
         } else {
             gr = *reinterpret_cast<const float4*>(a.g + i);
         }
@@ -116,7 +132,8 @@ int lah_adam_step(float* p, float* g, float* m, float* v, float* vmax, void* p_b
                   const long long* seg_n, int G,
                   const int* step, const int* group_rows, int step_scalar, float lr, float beta1, float beta2, float eps,
                   float weight_decay, int amsgrad, int zero_mask, int world, long long peer_grad_off,
-                  const unsigned long long* peer_bases, float grad_scale, cudaStream_t st) {
+                  const unsigned long long* peer_bases, float grad_scale, int G_active, const int* shadow_of,
+                  long long shadow_g_off, int me, cudaStream_t st) {
     if (num_segs < 1 || num_segs > 12) return -2;
     AdamArgs a;
     a.num_segs = num_segs;
@@ -134,6 +151,7 @@ int lah_adam_step(float* p, float* g, float* m, float* v, float* vmax, void* p_b
     a.total = off; a.step = step; a.group_rows = group_rows; a.step_scalar = step_scalar; a.lr = lr;
     a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.weight_decay = weight_decay; a.amsgrad = amsgrad;
     a.zero_mask = zero_mask; a.world = world; a.peer_grad_off = peer_grad_off; a.grad_scale = grad_scale;
+    a.G_active = G_active > 0 ? G_active : G; a.shadow_of = shadow_of; a.shadow_g_off = shadow_g_off; a.me = me;
     for (int i = 0; i < 8; ++i) a.peer_base[i] = (peer_bases && i < world) ? (char*)peer_bases[i] : nullptr;
     if (a.total <= 0) return 0;
     long long blocks = (a.total / 4 + 255) / 256;

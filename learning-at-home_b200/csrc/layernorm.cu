@@ -6,6 +6,7 @@
 //
 // Rows are grouped by expert in 128-row tiles; tile_group[t] gives the expert (or -1: tile unused, skipped).
 #include "sm100.cuh"
+#include <cuda_fp8.h>
 
 namespace lah {
 
@@ -15,11 +16,14 @@ constexpr float LN_EPS = 1e-5f;
 // forward: one warp per row, lane owns C/32 columns as chunks of 8 (coalesced 16B accesses)
 //   a = relu((h - mean) * rstd * gamma + beta);  saves mean / rstd per row
 // ------------------------------------------------------------------------------------------------
-template <int C>
+// With QUANT the kernel ALSO emits the MXFP8 operand of the next expert GEMM (csrc/grouped_gemm_fp8.cu): E4M3 payload +
+// one UE8M0 scale per 32 columns (4 adjacent lanes share a block: two shuffles), quantised from the fp32 value before it
+// is rounded to bf16.  The bf16 copy is optional (a == nullptr in forward-only runs).
+template <int C, bool QUANT>
 __global__ void __launch_bounds__(256, (C <= 2048) ? 3 : 1) ln_relu_fwd_kernel(
     const bf16* __restrict__ h, bf16* __restrict__ a, float* __restrict__ mean_out, float* __restrict__ rstd_out,
     const float* __restrict__ gamma, const float* __restrict__ beta, const int* __restrict__ tile_group, int rows,
-    int relu) {
+    int relu, uint8_t* __restrict__ aq, uint8_t* __restrict__ sf) {
     constexpr int NV = C / 256;  // int4 (8 x bf16) chunks per lane
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row = blockIdx.x * 8 + warp;
@@ -55,7 +59,7 @@ __global__ void __launch_bounds__(256, (C <= 2048) ? 3 : 1) ln_relu_fwd_kernel(
         }
     }
     const float rstd = rsqrtf(warp_sum(ss) * (1.f / C) + LN_EPS);
-    if (lane == 0) {
+    if (lane == 0 && mean_out) {
         mean_out[row] = mean;
         rstd_out[row] = rstd;
     }
@@ -83,12 +87,38 @@ __global__ void __launch_bounds__(256, (C <= 2048) ? 3 : 1) ln_relu_fwd_kernel(
 #pragma unroll
             for (int t = 0; t < 8; ++t) y[t] = fmaxf(y[t], 0.f);
         }
-        int4 o;
-        o.x = pack_bf16x2(y[0], y[1]);
-        o.y = pack_bf16x2(y[2], y[3]);
-        o.z = pack_bf16x2(y[4], y[5]);
-        o.w = pack_bf16x2(y[6], y[7]);
-        ap[j * 32 + lane] = o;
+        if (!QUANT || a) {
+            int4 o;
+            o.x = pack_bf16x2(y[0], y[1]);
+            o.y = pack_bf16x2(y[2], y[3]);
+            o.z = pack_bf16x2(y[4], y[5]);
+            o.w = pack_bf16x2(y[6], y[7]);
+            ap[j * 32 + lane] = o;
+        }
+        if (QUANT) {
+            float amax = 0.f;
+#pragma unroll
+            for (int t = 0; t < 8; ++t) amax = fmaxf(amax, fabsf(y[t]));
+            amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
+            amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
+            // smallest power-of-two scale with amax / scale <= 448 (same rule as quant_mxfp8_kernel)
+            const uint32_t bits = __float_as_uint(amax * (1.f / 448.f));
+            uint32_t e = ((bits >> 23) & 0xFFu) + ((bits & 0x7FFFFFu) ? 1u : 0u);
+            e = min(max(e, 1u), 253u);
+            const float inv = __uint_as_float((254u - e) << 23);
+            uint2 o8;
+            o8.x = static_cast<uint32_t>(__nv_cvt_float2_to_fp8x2(make_float2(y[0] * inv, y[1] * inv), __NV_SATFINITE, __NV_E4M3)) |
+                   (static_cast<uint32_t>(__nv_cvt_float2_to_fp8x2(make_float2(y[2] * inv, y[3] * inv), __NV_SATFINITE, __NV_E4M3)) << 16);
+            o8.y = static_cast<uint32_t>(__nv_cvt_float2_to_fp8x2(make_float2(y[4] * inv, y[5] * inv), __NV_SATFINITE, __NV_E4M3)) |
+                   (static_cast<uint32_t>(__nv_cvt_float2_to_fp8x2(make_float2(y[6] * inv, y[7] * inv), __NV_SATFINITE, __NV_E4M3)) << 16);
+            reinterpret_cast<uint2*>(aq + static_cast<long long>(row) * C)[j * 32 + lane] = o8;
+            if ((lane & 3) == 0) {
+                const int kb32 = j * 8 + (lane >> 2);   // 32-column block of this lane quad
+                const int ra = row & 127;
+                const long long chunk = static_cast<long long>(row >> 7) * (C / 128) + (kb32 >> 2);
+                sf[chunk * 512 + ((ra & 31) * 4 + (ra >> 5)) * 4 + (kb32 & 3)] = static_cast<uint8_t>(e);
+            }
+        }
     }
 }
 
@@ -287,8 +317,24 @@ int lah_ln_relu_fwd(const void* h, void* a, float* mean, float* rstd, const floa
     const int grid = (rows + 7) / 8;
 #define LAH_LN_FWD(CC)                                                                                          \
     if (C == CC) {                                                                                              \
-        ln_relu_fwd_kernel<CC><<<grid, 256, 0, st>>>((const bf16*)h, (bf16*)a, mean, rstd, gamma, beta,         \
-                                                     tile_group, rows, relu);                                   \
+        ln_relu_fwd_kernel<CC, false><<<grid, 256, 0, st>>>((const bf16*)h, (bf16*)a, mean, rstd, gamma, beta,  \
+                                                            tile_group, rows, relu, nullptr, nullptr);          \
+        return -(int)cudaGetLastError();                                                                        \
+    }
+    LAH_LN_FWD(256) LAH_LN_FWD(512) LAH_LN_FWD(1024) LAH_LN_FWD(2048) LAH_LN_FWD(4096)
+#undef LAH_LN_FWD
+    return -2;
+}
+
+// same + MXFP8 copy of the output (aq: e4m3 [rows, C]; sf: activation scale layout, tile_rows = 128); a may be NULL
+int lah_ln_relu_fwd_q(const void* h, void* a, float* mean, float* rstd, const float* gamma, const float* beta,
+                      const int* tile_group, int rows, int C, int relu, void* aq, void* sf, cudaStream_t st) {
+    if (rows <= 0) return 0;
+    const int grid = (rows + 7) / 8;
+#define LAH_LN_FWD(CC)                                                                                          \
+    if (C == CC) {                                                                                              \
+        ln_relu_fwd_kernel<CC, true><<<grid, 256, 0, st>>>((const bf16*)h, (bf16*)a, mean, rstd, gamma, beta,   \
+                                                           tile_group, rows, relu, (uint8_t*)aq, (uint8_t*)sf); \
         return -(int)cudaGetLastError();                                                                        \
     }
     LAH_LN_FWD(256) LAH_LN_FWD(512) LAH_LN_FWD(1024) LAH_LN_FWD(2048) LAH_LN_FWD(4096)

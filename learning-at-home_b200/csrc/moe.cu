@@ -195,17 +195,40 @@ struct LayoutArgs {
     int max_tiles;           // max_rows / 128
     int align;               // group padding in rows: 128 (1-CTA GEMM) or 256 (CTA-pair GEMM)
     int* counts;             // [E] local counts (zeroed on exit)
-    int* dst_row;            // [E]  row in the owner's buffer where MY first row for expert e goes
-    int* group_off;          // [E_loc + 1] padded offsets of my local experts
-    int* group_rows;         // [E_loc] valid rows of my local experts
+    int* dst_row;            // [E]  row (in route_owner[e]'s buffer) where MY first row for expert e goes
+    int* group_off;          // [E_loc + S_max + 1] padded offsets of my groups (owned experts, then shadow slots)
+    int* group_rows;         // [E_loc + S_max] valid rows of my groups
     int* tile_group;         // [max_tiles]
     int* total_rows;         // [1] padded rows in my buffer
     int* status;
+    // ---- hot-expert shadowing (dynamic data-parallel replicas; see the kernel comment)
+    int S_max;               // shadow slots per rank (0 disables)
+    float shadow_tol;        // stop once the most loaded rank is within tol x mean
+    int min_shadow_rows;     // never shadow an expert with fewer total rows
+    int* route_owner;        // [E]  rank whose buffer receives MY rows of expert e
+    int* step_rows;          // [E_loc] GLOBAL rows of my owned experts (optimizer gating)
+    int* shadow_info;        // [S_max][4]: expert (-1 = unused), owner, my rows in the slot (0 if I own it), rank mask
+    int* owned_shadow;       // [E_loc][2]: shadow slot of my owned expert (-1 = none), mask of ranks that have rows
 };
 
+constexpr int LAYOUT_MAX_E = 4096;
+
+// Load balancing.  Expert popularity is heavily skewed once training starts (a handful of experts receive most rows),
+// so a static expert -> GPU placement leaves most GPUs idle behind the owner of a hot expert.  After the count exchange
+// every rank knows the full [rank][expert] histogram and runs the SAME greedy selection: while the most loaded rank
+// exceeds tol x mean, its largest expert becomes a SHADOWED expert.  Rows routed to a shadowed expert are not dispatched:
+// every rank processes its own rows with a replica of the expert's weights (pulled from the owner over NVLink, see
+// pull_shadow_kernel) in one of its S_max shadow groups, and the owner's optimizer sums the partial weight gradients of
+// all ranks (adam.cu).  Shadowing an expert spreads its rows exactly like the tokens are spread (data parallel).
 __global__ void __launch_bounds__(1024) layout_exchange_kernel(Peers peers, LayoutArgs a) {
     __shared__ int warp_tot[32];
     __shared__ int owner_base_s[MAX_WORLD + 1];
+    __shared__ int s_tot[LAYOUT_MAX_E];
+    __shared__ short s_slot[LAYOUT_MAX_E];
+    __shared__ long long s_load[MAX_WORLD];
+    __shared__ int s_shadow[MAX_WORLD * 2];   // S_max <= 16
+    __shared__ int s_pick[2];
+    __shared__ int s_red_v[32], s_red_i[32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int me = peers.me, world = peers.world;
     // 1. publish my counts to every peer (plain P2P stores), then release the epoch flag on every peer
@@ -223,23 +246,99 @@ __global__ void __launch_bounds__(1024) layout_exchange_kernel(Peers peers, Layo
         spin_until_ge(fw, a.epoch, a.status);
     }
     for (int t = tid; t < a.max_tiles; t += blockDim.x) a.tile_group[t] = -1;
+    if (tid < MAX_WORLD) s_load[tid] = 0;
+    if (tid < MAX_WORLD * 2) s_shadow[tid] = -1;
     __syncthreads();
-    // 3. global layout, computed redundantly (and identically) on every rank:
+    const int* cnt_all = reinterpret_cast<const int*>(peers.base[me] + a.cnt_all_off);
+    // 3. totals per expert and the initial load of every rank (= rows of the experts it owns)
+    for (int e = tid; e < a.E; e += blockDim.x) {
+        int tot = 0;
+        for (int s = 0; s < world; ++s) tot += cnt_all[static_cast<long long>(s) * a.E + e];
+        s_tot[e] = tot;
+        s_slot[e] = -1;
+        if (tot) atomicAdd(reinterpret_cast<unsigned long long*>(&s_load[e / a.E_loc]), static_cast<unsigned long long>(tot));
+    }
+    __syncthreads();
+    // 4. greedy shadow selection (identical on every rank: same inputs, deterministic tie-breaks)
+    int num_shadow = 0;
+    for (int it = 0; it < a.S_max && world > 1; ++it) {
+        if (tid == 0) {
+            long long total = 0, mx = -1;
+            int rmax = 0;
+            for (int r = 0; r < world; ++r) {
+                total += s_load[r];
+                if (s_load[r] > mx) {
+                    mx = s_load[r];
+                    rmax = r;
+                }
+            }
+            const bool balanced = static_cast<float>(mx) * world <= a.shadow_tol * static_cast<float>(total);
+            s_pick[0] = balanced ? -1 : rmax;
+        }
+        __syncthreads();
+        const int rmax = s_pick[0];
+        if (rmax < 0) break;
+        // arg-max of tot[e] over the not yet shadowed experts of rank rmax (ties: smaller expert id)
+        int bv = -1, bi = -1;
+        for (int le = tid; le < a.E_loc; le += blockDim.x) {
+            const int e = rmax * a.E_loc + le;
+            if (s_slot[e] < 0 && s_tot[e] > bv) {
+                bv = s_tot[e];
+                bi = e;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const int ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > bv || (ov == bv && oi >= 0 && (bi < 0 || oi < bi))) {
+                bv = ov;
+                bi = oi;
+            }
+        }
+        if (lane == 0) {
+            s_red_v[warp] = bv;
+            s_red_i[warp] = bi;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int v = -1, i = -1;
+            for (int w = 0; w < 32; ++w)
+                if (s_red_v[w] > v || (s_red_v[w] == v && s_red_i[w] >= 0 && (i < 0 || s_red_i[w] < i))) {
+                    v = s_red_v[w];
+                    i = s_red_i[w];
+                }
+            if (i < 0 || v < a.min_shadow_rows) {
+                s_pick[1] = -1;
+            } else {
+                s_pick[1] = i;
+                s_slot[i] = static_cast<short>(it);
+                s_shadow[it] = i;
+                s_load[rmax] -= v;
+                for (int r = 0; r < world; ++r) s_load[r] += cnt_all[static_cast<long long>(r) * a.E + i];
+            }
+        }
+        __syncthreads();
+        if (s_pick[1] < 0) break;
+        ++num_shadow;
+    }
+    // 5. layout of the OWNED groups of every rank, computed redundantly (and identically) everywhere:
+    //    rows(e) = all rows of e, or only the owner's own rows when e is shadowed
     //    dst_row[e] <- exclusive prefix of padded group sizes over ALL experts (temporarily),
     //    counts[e]  <- rows of expert e that come from ranks < me (the local counts are consumed by now)
-    const int* cnt_all = reinterpret_cast<const int*>(peers.base[me] + a.cnt_all_off);
     int running = 0;
     for (int chunk = 0; chunk < a.E; chunk += blockDim.x) {
         const int e = chunk + tid;
-        int tot = 0, before = 0;
+        int rows = 0, before = 0;
         if (e < a.E) {
-            for (int s = 0; s < world; ++s) {
-                const int c = cnt_all[static_cast<long long>(s) * a.E + e];
-                tot += c;
-                if (s < me) before += c;
+            if (s_slot[e] >= 0) {
+                rows = cnt_all[static_cast<long long>(e / a.E_loc) * a.E + e];
+            } else {
+                rows = s_tot[e];
+                for (int s = 0; s < me; ++s) before += cnt_all[static_cast<long long>(s) * a.E + e];
             }
         }
-        const int padded = (tot + a.align - 1) / a.align * a.align;
+        const int padded = (rows + a.align - 1) / a.align * a.align;
         int v = padded;  // inclusive scan inside the warp
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -263,34 +362,80 @@ __global__ void __launch_bounds__(1024) layout_exchange_kernel(Peers peers, Layo
         if (e < a.E) {
             a.dst_row[e] = excl;
             a.counts[e] = before;
-            if (e / a.E_loc == me) a.group_rows[e - me * a.E_loc] = tot;
+            if (e / a.E_loc == me) a.group_rows[e - me * a.E_loc] = rows;
         }
         __syncthreads();
     }
     if (tid < world) owner_base_s[tid] = a.dst_row[tid * a.E_loc];
     if (tid == 0) owner_base_s[world] = running;
     __syncthreads();
-    // 4. make offsets owner-relative; fill the tables of my local experts
+    // 6. my shadow groups follow my owned groups; every rank's total is checked against the buffer capacity
+    const int G_own = a.E_loc;
+    if (tid == 0) {
+        int cur = owner_base_s[me + 1] - owner_base_s[me];
+        for (int s = 0; s < a.S_max; ++s) {
+            const int e = s_shadow[s];
+            const int rows = (e >= 0 && e / a.E_loc != me) ? cnt_all[static_cast<long long>(me) * a.E + e] : 0;
+            const int padded = (rows + a.align - 1) / a.align * a.align;
+            a.group_off[G_own + s] = cur;
+            a.group_rows[G_own + s] = rows;
+            for (int t = cur / 128; t < (cur + padded) / 128 && t < a.max_tiles; ++t) a.tile_group[t] = G_own + s;
+            int mask = 0;
+            if (e >= 0)
+                for (int r = 0; r < world; ++r) mask |= (cnt_all[static_cast<long long>(r) * a.E + e] > 0) << r;
+            a.shadow_info[4 * s + 0] = e;
+            a.shadow_info[4 * s + 1] = e >= 0 ? e / a.E_loc : -1;
+            a.shadow_info[4 * s + 2] = rows;
+            a.shadow_info[4 * s + 3] = mask;
+            cur += padded;
+        }
+        a.group_off[G_own + a.S_max] = cur;
+        *a.total_rows = cur;
+    }
+    if (tid < world) {
+        int total = owner_base_s[tid + 1] - owner_base_s[tid];
+        for (int s = 0; s < a.S_max; ++s) {
+            const int e = s_shadow[s];
+            if (e >= 0 && e / a.E_loc != tid)
+                total += (cnt_all[static_cast<long long>(tid) * a.E + e] + a.align - 1) / a.align * a.align;
+        }
+        if (total > a.max_rows) atomicOr(a.status, STATUS_OVERFLOW);
+    }
+    __syncthreads();
+    // 7. make offsets owner-relative; routing tables; tables of my owned experts
     for (int e = tid; e < a.E; e += blockDim.x) {
         const int owner = e / a.E_loc;
         const int rel = a.dst_row[e] - owner_base_s[owner];
         const int before = a.counts[e];
+        const int slot = s_slot[e];
         a.counts[e] = 0;  // leave the slot counters clean for the next gate call
         if (owner == me) {
             const int le = e - me * a.E_loc;
             a.group_off[le] = rel;
             const int padded = (a.group_rows[le] + a.align - 1) / a.align * a.align;
             for (int t = rel / 128; t < (rel + padded) / 128 && t < a.max_tiles; ++t) a.tile_group[t] = le;
+            if (a.step_rows) a.step_rows[le] = s_tot[e];
+            if (a.owned_shadow) {
+                int mask = 0;
+                if (slot >= 0)
+                    for (int r = 0; r < world; ++r) mask |= (cnt_all[static_cast<long long>(r) * a.E + e] > 0) << r;
+                a.owned_shadow[2 * le] = slot;
+                a.owned_shadow[2 * le + 1] = mask;
+            }
         }
-        a.dst_row[e] = rel + before;
-    }
-    if (tid == 0) {
-        const int total = owner_base_s[me + 1] - owner_base_s[me];
-        a.group_off[a.E_loc] = total;
-        *a.total_rows = total;
-        bool overflow = false;
-        for (int r = 0; r < world; ++r) overflow |= (owner_base_s[r + 1] - owner_base_s[r]) > a.max_rows;
-        if (overflow) atomicOr(a.status, STATUS_OVERFLOW);
+        int dst, route;
+        if (slot < 0) {
+            dst = rel + before;
+            route = owner;
+        } else if (owner == me) {
+            dst = rel;
+            route = me;
+        } else {
+            dst = a.group_off[G_own + slot];
+            route = me;
+        }
+        a.dst_row[e] = dst;
+        if (a.route_owner) a.route_owner[e] = route;
     }
 }
 
@@ -313,6 +458,8 @@ struct ScatterArgs {
     const int* group_rows;
     int pair_blocks;          // CTAs that handle pairs; the rest zero padding
     int align;                // group padding in rows
+    const int* route_owner;   // [E] destination rank of MY rows of expert e (nullptr: the owner e / E_loc)
+    int num_groups;           // groups in my buffer (owned experts + shadow slots) whose padding rows are zeroed
     int* done_counter;
     int* status;
 };
@@ -334,7 +481,7 @@ __global__ void __launch_bounds__(256) scatter_rows_kernel(Peers peers, ScatterA
             }
             if (a.pair_row && a.dst_row && lane == 0) a.pair_row[p] = row;
             if (row >= 0) {
-                const int owner = e / a.E_loc;
+                const int owner = a.route_owner ? a.route_owner[e] : e / a.E_loc;
                 const int b = p / a.k;
                 const int4* sp = reinterpret_cast<const int4*>(a.src + static_cast<long long>(b) * a.H);
                 int4* dp = reinterpret_cast<int4*>(peers.base[owner] + a.dst_off) +
@@ -363,7 +510,7 @@ __global__ void __launch_bounds__(256) scatter_rows_kernel(Peers peers, ScatterA
         const int nb = gridDim.x - a.pair_blocks;
         int4* base = reinterpret_cast<int4*>(peers.base[peers.me] + a.dst_off);
         const int4 z = make_int4(0, 0, 0, 0);
-        for (int le = blockIdx.x - a.pair_blocks; le < a.E_loc; le += nb) {
+        for (int le = blockIdx.x - a.pair_blocks; le < a.num_groups; le += nb) {
             const int r0 = a.group_off[le] + a.group_rows[le];
             const int r1 = min(a.max_rows, a.group_off[le] + (a.group_rows[le] + a.align - 1) / a.align * a.align);
             for (int r = r0 + warp; r < r1; r += 8) {
@@ -420,6 +567,7 @@ struct CombineArgs {
     long long flags_off;
     int slot, epoch, do_signal, do_wait;
     int* status;
+    const int* route_owner;   // [E] rank that holds MY rows of expert e (nullptr: e / E_loc)
 };
 
 template <int VEC_PER_LANE>
@@ -449,7 +597,7 @@ __global__ void __launch_bounds__(256) combine_rows_kernel(Peers peers, CombineA
         const int row = a.pair_row[p];
         if (e < 0 || row < 0) continue;
         const float w = a.w ? a.w[p] : 1.f;
-        const int4* sp = reinterpret_cast<const int4*>(peers.base[e / a.E_loc] + a.src_off) +
+        const int4* sp = reinterpret_cast<const int4*>(peers.base[a.route_owner ? a.route_owner[e] : e / a.E_loc] + a.src_off) +
                          static_cast<long long>(row) * (a.H / 8);
 #pragma unroll
         for (int v = 0; v < VEC_PER_LANE; ++v) {
@@ -487,6 +635,7 @@ struct GateBwdArgs {
     const float* w;
     float* dlogits;           // [B, gs.total]
     int B, k, H, E_loc;
+    const int* route_owner;   // [E] or nullptr
 };
 
 template <int VEC_PER_LANE>
@@ -520,7 +669,7 @@ __global__ void __launch_bounds__(256) gate_bwd_kernel(Peers peers, GateBwdArgs 
             const int e = a.idx[p];
             const int row = a.pair_row[p];
             if (e >= 0 && row >= 0) {
-                const int4* sp = reinterpret_cast<const int4*>(peers.base[e / a.E_loc] + a.yo_off) +
+                const int4* sp = reinterpret_cast<const int4*>(peers.base[a.route_owner ? a.route_owner[e] : e / a.E_loc] + a.yo_off) +
                                  static_cast<long long>(row) * (a.H / 8);
                 float d = 0.f;
 #pragma unroll
@@ -557,6 +706,57 @@ __global__ void __launch_bounds__(256) gate_bwd_kernel(Peers peers, GateBwdArgs 
             }
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// shadow replicas: pull the parameters of the shadowed experts from their owners (P2P loads over NVLink)
+// Flat parameter layout (ExpertShard): segment sg holds [slots, seg_n[sg]] values starting at seg_start[sg]; slots =
+// E_loc owned experts followed by S_max shadow slots.  Big segments (weights) are pulled from the bf16 mirror that the
+// GEMMs consume, small ones (biases, LayerNorm affine) from the fp32 master copy.
+// ------------------------------------------------------------------------------------------------
+struct SegLayout {
+    int num_segs;
+    long long seg_start[13];
+    long long seg_n[12];
+};
+
+struct PullArgs {
+    const int* shadow_info;   // [S_max][4] written by layout_exchange
+    int E_loc;
+    long long p_off, pbf16_off;  // symmetric offsets of the fp32 parameters / bf16 mirror
+    SegLayout L;
+    int small_mask;           // bit sg: segment sg is a small fp32 parameter
+};
+
+__global__ void __launch_bounds__(256) pull_shadow_kernel(Peers peers, PullArgs a) {
+    const int s = blockIdx.y;
+    const int e = a.shadow_info[4 * s + 0], owner = a.shadow_info[4 * s + 1], rows = a.shadow_info[4 * s + 2];
+    if (e < 0 || owner == peers.me || rows <= 0) return;
+    const int le = e - owner * a.E_loc;
+    const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const long long nthreads = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (int sg = 0; sg < a.L.num_segs; ++sg) {
+        const long long n = a.L.seg_n[sg];
+        const bool small = (a.small_mask >> sg) & 1;
+        const long long esz = small ? 4 : 2;
+        const long long off = small ? a.p_off : a.pbf16_off;
+        const int4* src = reinterpret_cast<const int4*>(peers.base[owner] + off + (a.L.seg_start[sg] + le * n) * esz);
+        int4* dst = reinterpret_cast<int4*>(peers.base[peers.me] + off + (a.L.seg_start[sg] + (a.E_loc + s) * n) * esz);
+        const long long nvec = n * esz / 16;
+#pragma unroll 4
+        for (long long v = tid; v < nvec; v += nthreads) dst[v] = ld_v4(src + v);
+    }
+}
+
+// zero the gradient slots [first_slot, first_slot + num_slots) of the segments selected by seg_mask
+__global__ void __launch_bounds__(256) zero_slots_kernel(float* g, SegLayout L, int first_slot, int num_slots, int seg_mask) {
+    const int sg = blockIdx.y;
+    if (!((seg_mask >> sg) & 1)) return;
+    float4* base = reinterpret_cast<float4*>(g + L.seg_start[sg] + first_slot * L.seg_n[sg]);
+    const long long nvec = num_slots * L.seg_n[sg] / 4;
+    for (long long v = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; v < nvec;
+         v += static_cast<long long>(gridDim.x) * blockDim.x)
+        base[v] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
 static Peers g_peers = {};
@@ -608,12 +808,16 @@ int lah_gate_topk(const float* logits, int B, const int* grid, int ndim, int k, 
 
 int lah_layout_exchange(long long cnt_all_off, long long flags_off, int slot, int epoch, int E, int E_loc, int max_rows,
                         int align, int* counts, int* dst_row, int* group_off, int* group_rows, int* tile_group, int* total_rows,
-                        int* status, cudaStream_t st) {
+                        int* status, int S_max, float shadow_tol, int min_shadow_rows, int* route_owner, int* step_rows,
+                        int* shadow_info, int* owned_shadow, cudaStream_t st) {
     if (!g_peers_set) return -10;
+    if (E > LAYOUT_MAX_E || S_max < 0 || S_max > 2 * MAX_WORLD) return -2;
     LayoutArgs a;
     a.cnt_all_off = cnt_all_off; a.flags_off = flags_off; a.slot = slot; a.epoch = epoch; a.E = E; a.E_loc = E_loc;
     a.max_rows = max_rows; a.max_tiles = max_rows / 128; a.align = align; a.counts = counts; a.dst_row = dst_row; a.group_off = group_off;
     a.group_rows = group_rows; a.tile_group = tile_group; a.total_rows = total_rows; a.status = status;
+    a.S_max = S_max; a.shadow_tol = shadow_tol; a.min_shadow_rows = min_shadow_rows; a.route_owner = route_owner;
+    a.step_rows = step_rows; a.shadow_info = shadow_info; a.owned_shadow = owned_shadow;
     layout_exchange_kernel<<<1, 1024, 0, st>>>(g_peers, a);
     return -(int)cudaGetLastError();
 }
@@ -621,14 +825,15 @@ int lah_layout_exchange(long long cnt_all_off, long long flags_off, int slot, in
 int lah_scatter_rows(const void* src, const float* scale, const int* idx, const int* pos, const int* dst_row,
                      int* pair_row, long long dst_off, long long flags_off, int slot, int epoch, int num_pairs, int k,
                      int H, int E_loc, int max_rows, int align, const int* group_off, const int* group_rows,
-                     int* done_counter, int* status, cudaStream_t st) {
+                     int* done_counter, int* status, const int* route_owner, int num_groups, cudaStream_t st) {
     if (!g_peers_set) return -10;
     ScatterArgs a;
     a.src = (const bf16*)src; a.scale = scale; a.idx = idx; a.pos = pos; a.dst_row = dst_row; a.pair_row = pair_row;
     a.dst_off = dst_off; a.flags_off = flags_off; a.slot = slot; a.epoch = epoch; a.num_pairs = num_pairs; a.k = k;
     a.H = H; a.E_loc = E_loc; a.max_rows = max_rows; a.group_off = group_off; a.group_rows = group_rows;
     a.pair_blocks = (num_pairs + 7) / 8; a.align = align; a.done_counter = done_counter; a.status = status;
-    const int pad_blocks = E_loc < 64 ? E_loc : 64;
+    a.route_owner = route_owner; a.num_groups = num_groups > 0 ? num_groups : E_loc;
+    const int pad_blocks = a.num_groups < 64 ? a.num_groups : 64;
     const int grid = a.pair_blocks + pad_blocks;
     if (H == 256) scatter_rows_kernel<1><<<grid, 256, 0, st>>>(g_peers, a);
     else if (H == 512) scatter_rows_kernel<2><<<grid, 256, 0, st>>>(g_peers, a);
@@ -646,13 +851,13 @@ int lah_signal_wait(long long flags_off, int slot, int epoch, int do_signal, int
 
 int lah_combine_rows(long long src_off, const int* idx, const int* pair_row, const float* w, void* out, int B, int k,
                      int H, int E_loc, long long flags_off, int slot, int epoch, int do_signal, int do_wait, int* status,
-                     cudaStream_t st) {
+                     const int* route_owner, cudaStream_t st) {
     if (!g_peers_set) return -10;
     if (B <= 0) return 0;
     CombineArgs a;
     a.src_off = src_off; a.idx = idx; a.pair_row = pair_row; a.w = w; a.out = (bf16*)out; a.B = B; a.k = k; a.H = H;
     a.E_loc = E_loc; a.flags_off = flags_off; a.slot = slot; a.epoch = epoch; a.do_signal = do_signal; a.do_wait = do_wait;
-    a.status = status;
+    a.status = status; a.route_owner = route_owner;
     const int grid = (B + 7) / 8;
     if (H == 256) combine_rows_kernel<1><<<grid, 256, 0, st>>>(g_peers, a);
     else if (H == 512) combine_rows_kernel<2><<<grid, 256, 0, st>>>(g_peers, a);
@@ -662,7 +867,8 @@ int lah_combine_rows(long long src_off, const int* idx, const int* pair_row, con
 }
 
 int lah_gate_bwd(long long yo_off, const void* grad, const int* idx, const int* pair_row, const float* w,
-                 float* dlogits, int B, int k, int H, int E_loc, const int* grid_sizes, int ndim, cudaStream_t st) {
+                 float* dlogits, int B, int k, int H, int E_loc, const int* grid_sizes, int ndim, const int* route_owner,
+                 cudaStream_t st) {
     if (!g_peers_set) return -10;
     if (B <= 0) return 0;
     GridSpec gs;
@@ -670,12 +876,48 @@ int lah_gate_bwd(long long yo_off, const void* grad, const int* idx, const int* 
     if (k > MAX_K) return -3;
     GateBwdArgs a;
     a.yo_off = yo_off; a.grad = (const bf16*)grad; a.idx = idx; a.pair_row = pair_row; a.w = w; a.dlogits = dlogits;
-    a.B = B; a.k = k; a.H = H; a.E_loc = E_loc;
+    a.B = B; a.k = k; a.H = H; a.E_loc = E_loc; a.route_owner = route_owner;
     const int grid = (B + 7) / 8;
     if (H == 256) gate_bwd_kernel<1><<<grid, 256, 0, st>>>(g_peers, a, gs);
     else if (H == 512) gate_bwd_kernel<2><<<grid, 256, 0, st>>>(g_peers, a, gs);
     else if (H == 1024) gate_bwd_kernel<4><<<grid, 256, 0, st>>>(g_peers, a, gs);
     else return -2;
+    return -(int)cudaGetLastError();
+}
+
+static int make_seg_layout(SegLayout* L, int num_segs, const long long* seg_n, int slots) {
+    if (num_segs < 1 || num_segs > 12) return -2;
+    L->num_segs = num_segs;
+    long long off = 0;
+    for (int s = 0; s < 12; ++s) {
+        L->seg_start[s] = off;
+        L->seg_n[s] = s < num_segs ? seg_n[s] : 8;
+        if (s < num_segs) {
+            if (seg_n[s] % 8) return -2;
+            off += seg_n[s] * slots;
+        }
+    }
+    L->seg_start[12] = off;
+    return 0;
+}
+
+int lah_pull_shadow(const int* shadow_info, int S_max, int E_loc, long long p_off, long long pbf16_off, int num_segs,
+                    const long long* seg_n, int small_mask, cudaStream_t st) {
+    if (!g_peers_set) return -10;
+    if (S_max <= 0) return 0;
+    PullArgs a;
+    a.shadow_info = shadow_info; a.E_loc = E_loc; a.p_off = p_off; a.pbf16_off = pbf16_off; a.small_mask = small_mask;
+    if (make_seg_layout(&a.L, num_segs, seg_n, E_loc + S_max)) return -2;
+    pull_shadow_kernel<<<dim3(64, S_max), 256, 0, st>>>(g_peers, a);
+    return -(int)cudaGetLastError();
+}
+
+int lah_zero_slots(float* g, int num_segs, const long long* seg_n, int slots, int first_slot, int num_slots, int seg_mask,
+                   cudaStream_t st) {
+    if (num_slots <= 0) return 0;
+    SegLayout L;
+    if (make_seg_layout(&L, num_segs, seg_n, slots)) return -2;
+    zero_slots_kernel<<<dim3(8, num_segs), 256, 0, st>>>(g, L, first_slot, num_slots, seg_mask);
     return -(int)cudaGetLastError();
 }
 

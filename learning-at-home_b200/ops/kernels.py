@@ -13,7 +13,7 @@ from .native import c_void_p, c_int, c_ll, c_float, ptr, stream_ptr
 c_ull = ctypes.c_ulonglong
 _configured = False
 
-SLOT_COUNTS, SLOT_DISPATCH, SLOT_OUTPUT, SLOT_GRAD, SLOT_DINPUT, SLOT_TRAINER, SLOT_BARRIER = range(7)
+SLOT_COUNTS, SLOT_DISPATCH, SLOT_OUTPUT, SLOT_GRAD, SLOT_DINPUT, SLOT_TRAINER, SLOT_BARRIER, SLOT_SHADOW = range(8)
 NUM_SLOTS = 8
 MAX_WORLD = 8
 STATUS_TIMEOUT, STATUS_OVERFLOW = 1, 2
@@ -27,16 +27,19 @@ def _lib():
     P, I, L, Fl = c_void_p, c_int, c_ll, c_float
     sigs = {
         "lah_ln_relu_fwd": [P, P, P, P, P, P, P, I, I, I, P],
+        "lah_ln_relu_fwd_q": [P, P, P, P, P, P, P, I, I, I, P, P, P],
         "lah_ln_relu_bwd": [P, P, P, P, P, P, P, P, P, P, P, I, I, I, P],
         "lah_grouped_colsum": [P, L, P, I, P, I, P],
         "lah_set_peers": [P, I, I],
         "lah_gate_topk": [P, I, P, I, I, P, Fl, c_ull, L, P, P, P, P, P],
-        "lah_layout_exchange": [L, L, I, I, I, I, I, I, P, P, P, P, P, P, P, P],
-        "lah_scatter_rows": [P, P, P, P, P, P, L, L, I, I, I, I, I, I, I, I, P, P, P, P, P],
+        "lah_layout_exchange": [L, L, I, I, I, I, I, I, P, P, P, P, P, P, P, I, Fl, I, P, P, P, P, P],
+        "lah_scatter_rows": [P, P, P, P, P, P, L, L, I, I, I, I, I, I, I, I, P, P, P, P, P, I, P],
+        "lah_pull_shadow": [P, I, I, L, L, I, P, I, P],
+        "lah_zero_slots": [P, I, P, I, I, I, I, P],
         "lah_signal_wait": [L, I, I, I, I, P, P],
-        "lah_combine_rows": [L, P, P, P, P, I, I, I, I, L, I, I, I, I, P, P],
-        "lah_gate_bwd": [L, P, P, P, P, P, I, I, I, I, P, I, P],
-        "lah_adam_step": [P, P, P, P, P, P, I, P, I, P, P, I, Fl, Fl, Fl, Fl, Fl, I, I, I, L, P, Fl, P],
+        "lah_combine_rows": [L, P, P, P, P, I, I, I, I, L, I, I, I, I, P, P, P],
+        "lah_gate_bwd": [L, P, P, P, P, P, I, I, I, I, P, I, P, P],
+        "lah_adam_step": [P, P, P, P, P, P, I, P, I, P, P, I, Fl, Fl, Fl, Fl, Fl, I, I, I, L, P, Fl, I, P, L, I, P],
         "lah_bump_steps": [P, P, I, P],
         "lah_cast_bf16": [P, P, L, P],
         "lah_attention_fwd": [P, P, I, I, I, P],
@@ -62,11 +65,19 @@ def _grid_array(grid_size):
 # ---------------------------------------------------------------------------------------------------------
 # LayerNorm + ReLU over expert-grouped rows
 # ---------------------------------------------------------------------------------------------------------
-def ln_relu_fwd(h, gamma, beta, tile_group, *, out, mean, rstd, relu=True):
+def ln_relu_fwd(h, gamma, beta, tile_group, *, out, mean, rstd, relu=True, quant=None):
+    """:param quant: optional ops.fp8.MXFP8Tensor that additionally receives the output as an MXFP8 GEMM operand
+    (``out`` may then be None: forward-only runs do not need the bf16 copy)"""
     rows, C = h.shape
-    assert h.is_contiguous() and out.is_contiguous() and gamma.dtype == torch.float32
-    native.check(_lib().lah_ln_relu_fwd(ptr(h), ptr(out), ptr(mean), ptr(rstd), ptr(gamma), ptr(beta), ptr(tile_group),
-                                        rows, C, int(relu), stream_ptr()), "lah_ln_relu_fwd")
+    assert h.is_contiguous() and gamma.dtype == torch.float32 and (out is None or out.is_contiguous())
+    if quant is not None:
+        assert quant.K == C and quant.groups == 1 and quant.rows_per_group >= rows and quant.tile_rows == 128
+        native.check(_lib().lah_ln_relu_fwd_q(ptr(h), ptr(out), ptr(mean), ptr(rstd), ptr(gamma), ptr(beta),
+                                              ptr(tile_group), rows, C, int(relu), ptr(quant.q), ptr(quant.sf),
+                                              stream_ptr()), "lah_ln_relu_fwd_q")
+    else:
+        native.check(_lib().lah_ln_relu_fwd(ptr(h), ptr(out), ptr(mean), ptr(rstd), ptr(gamma), ptr(beta),
+                                            ptr(tile_group), rows, C, int(relu), stream_ptr()), "lah_ln_relu_fwd")
     native.count_launch()
     return out
 
@@ -107,21 +118,41 @@ def gate_topk(logits, grid_size, k, *, alive=None, failure_rate=0.0, seed=0, tok
 
 
 def layout_exchange(cnt_all_off, flags_off, slot, epoch, E, E_loc, max_rows, *, align=128, counts, dst_row, group_off, group_rows,
-                    tile_group, total_rows, status):
+                    tile_group, total_rows, status, shadow_slots=0, shadow_tol=1.1, min_shadow_rows=512, route_owner=None,
+                    step_rows=None, shadow_info=None, owned_shadow=None):
+    """count exchange + global layout; with ``shadow_slots`` > 0 also the hot-expert shadow selection (csrc/moe.cu)"""
     native.check(_lib().lah_layout_exchange(cnt_all_off, flags_off, slot, epoch, E, E_loc, max_rows, align, ptr(counts),
                                             ptr(dst_row), ptr(group_off), ptr(group_rows), ptr(tile_group),
-                                            ptr(total_rows), ptr(status), stream_ptr()), "lah_layout_exchange")
+                                            ptr(total_rows), ptr(status), int(shadow_slots), float(shadow_tol),
+                                            int(min_shadow_rows), ptr(route_owner), ptr(step_rows), ptr(shadow_info),
+                                            ptr(owned_shadow), stream_ptr()), "lah_layout_exchange")
+    native.count_launch()
+
+
+def pull_shadow(shadow_info, shadow_slots, E_loc, p_off, pbf16_off, seg_sizes, small_mask):
+    """replicate the parameters of the shadowed experts from their owners into my shadow slots (P2P loads)"""
+    segs = (c_ll * len(seg_sizes))(*[int(s) for s in seg_sizes])
+    native.check(_lib().lah_pull_shadow(ptr(shadow_info), int(shadow_slots), E_loc, p_off, pbf16_off, len(seg_sizes),
+                                        ctypes.cast(segs, c_void_p), int(small_mask), stream_ptr()), "lah_pull_shadow")
+    native.count_launch()
+
+
+def zero_slots(g, seg_sizes, slots, first_slot, num_slots, seg_mask):
+    segs = (c_ll * len(seg_sizes))(*[int(s) for s in seg_sizes])
+    native.check(_lib().lah_zero_slots(ptr(g), len(seg_sizes), ctypes.cast(segs, c_void_p), slots, first_slot, num_slots,
+                                       int(seg_mask), stream_ptr()), "lah_zero_slots")
     native.count_launch()
 
 
 def scatter_rows(src, scale, idx, pos, dst_row, pair_row, dst_off, flags_off, slot, epoch, k, E_loc, max_rows,
-                 group_off, group_rows, done_counter, status, align=128):
+                 group_off, group_rows, done_counter, status, align=128, route_owner=None, num_groups=0):
     num_pairs = idx.numel()
     H = src.shape[1]
     assert src.is_contiguous() and src.dtype == torch.bfloat16
     native.check(_lib().lah_scatter_rows(ptr(src), ptr(scale), ptr(idx), ptr(pos), ptr(dst_row), ptr(pair_row), dst_off,
                                          flags_off, slot, epoch, num_pairs, k, H, E_loc, max_rows, align, ptr(group_off),
-                                         ptr(group_rows), ptr(done_counter), ptr(status), stream_ptr()),
+                                         ptr(group_rows), ptr(done_counter), ptr(status), ptr(route_owner),
+                                         int(num_groups), stream_ptr()),
                  "lah_scatter_rows")
     native.count_launch()
 
@@ -133,22 +164,24 @@ def signal_wait(flags_off, slot, epoch, status, *, signal=True, wait=True):
 
 
 def combine_rows(src_off, idx, pair_row, w, out, k, E_loc, *, flags_off=0, slot=0, epoch=0, signal=False, wait=False,
-                 status=None):
+                 status=None, route_owner=None):
     """weighted P2P gather; with signal/wait the kernel itself publishes 'my expert outputs are ready' to every peer
     and waits for all peers' flags before pulling their rows (no separate flag kernels)"""
     B, H = out.shape
     native.check(_lib().lah_combine_rows(src_off, ptr(idx), ptr(pair_row), ptr(w), ptr(out), B, k, H, E_loc, flags_off,
-                                         slot, epoch, int(signal), int(wait), ptr(status), stream_ptr()),
+                                         slot, epoch, int(signal), int(wait), ptr(status), ptr(route_owner),
+                                         stream_ptr()),
                  "lah_combine_rows")
     native.count_launch()
     return out
 
 
-def gate_bwd(yo_off, grad, idx, pair_row, w, dlogits, k, E_loc, grid_size):
+def gate_bwd(yo_off, grad, idx, pair_row, w, dlogits, k, E_loc, grid_size, route_owner=None):
     B, H = grad.shape
     assert grad.is_contiguous() and grad.dtype == torch.bfloat16 and dlogits.dtype == torch.float32
     native.check(_lib().lah_gate_bwd(yo_off, ptr(grad), ptr(idx), ptr(pair_row), ptr(w), ptr(dlogits), B, k, H, E_loc,
-                                     ctypes.cast(_grid_array(grid_size), c_void_p), len(grid_size), stream_ptr()),
+                                     ctypes.cast(_grid_array(grid_size), c_void_p), len(grid_size), ptr(route_owner),
+                                     stream_ptr()),
                  "lah_gate_bwd")
     native.count_launch()
     return dlogits
@@ -189,7 +222,7 @@ def attention_ref(qkv, num_heads, seq_len=512):
 # ---------------------------------------------------------------------------------------------------------
 def adam_step(p, g, m, v, vmax, p_bf16, seg_sizes, G, *, step=None, group_rows=None, step_scalar=0, lr=1e-3,
               betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, amsgrad=True, zero_mask=0, world=1,
-              peer_grad_off=-1, peer_bases=None, grad_scale=1.0):
+              peer_grad_off=-1, peer_bases=None, grad_scale=1.0, G_active=0, shadow_of=None, shadow_g_off=-1, me=0):
     arr = None
     if peer_bases is not None:
         arr = (c_ull * len(peer_bases))(*[int(b) for b in peer_bases])
@@ -197,6 +230,9 @@ def adam_step(p, g, m, v, vmax, p_bf16, seg_sizes, G, *, step=None, group_rows=N
     One fused Adam/AMSGrad step over a flat fp32 buffer laid out as consecutive segments [G, seg_sizes[s]].
     :param step: int32 [G] per-group step counts (already incremented) or None -> step_scalar for everything
     :param group_rows: int32 [G]; groups with 0 rows are skipped (experts that received no tokens are not stepped)
+    :param G_active: only the first G_active of the G slots per segment are updated (the rest are shadow replicas)
+    :param shadow_of: int32 [G_active, 2] (slot, rank mask): gradient of a shadowed expert = sum of the partial
+        gradients in shadow slot ``slot`` of the ranks in ``mask`` (buffers at symmetric offset ``shadow_g_off``)
     """
     if isinstance(seg_sizes, int):
         seg_sizes = [seg_sizes]
@@ -206,6 +242,7 @@ def adam_step(p, g, m, v, vmax, p_bf16, seg_sizes, G, *, step=None, group_rows=N
                                       ptr(group_rows), int(step_scalar), lr, betas[0], betas[1], eps, weight_decay,
                                       int(amsgrad), int(zero_mask), world, peer_grad_off,
                                       ctypes.cast(arr, c_void_p) if arr is not None else c_void_p(0), grad_scale,
+                                      int(G_active), ptr(shadow_of), int(shadow_g_off), int(me),
                                       stream_ptr()), "lah_adam_step")
     native.count_launch()
 

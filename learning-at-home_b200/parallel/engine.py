@@ -25,7 +25,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from ..ops import gemm, kernels as K, native
+from ..ops import fp8, gemm, kernels as K, native
 
 SEG_NAMES = ("w1", "b1", "g1", "be1", "w2", "b2", "g2", "be2", "w3", "b3")
 #: name of each segment inside a reference FeedforwardBlock state_dict (layers.py:8-16)
@@ -59,6 +59,15 @@ class DMoEConfig:
     #                  like in the reference emulator these gate parameters are NOT trained (get_non_expert_params excludes
     #                  them and no expert optimizer owns them); requires a 1-d grid (grid_size=(num_experts,))
     gate_mode: str = "product_key"
+    # hot-expert shadowing (multi-GPU load balancing, csrc/moe.cu layout_exchange_kernel): up to `shadow_experts` experts
+    # per layer and step are processed data-parallel (every rank keeps its own rows and a replica of the weights, the
+    # owner's optimizer sums the partial gradients); selection stops once max rank load <= shadow_tol * mean
+    shadow_experts: int = 8
+    shadow_tol: float = 1.1
+    shadow_min_rows: int = 1024
+    # "bf16" or "fp8": with "fp8" the three forward GEMMs of every expert run on block-scaled FP8 tensor cores (MXFP8:
+    # E4M3 + UE8M0 scale per 1x32 block, csrc/grouped_gemm_fp8.cu); dgrad / wgrad / optimizer are unchanged (bf16 / fp32)
+    expert_dtype: str = "bf16"
 
     @property
     def num_experts(self) -> int:
@@ -106,11 +115,16 @@ class EngineContext:
         self.two_cta = cfg.two_cta and os.environ.get("LAH_TWO_CTA", "1") != "0" and cfg.inner % 256 == 0 \
             and cfg.hidden % 256 == 0
         self.align = 256 if self.two_cta else 128   # expert groups are padded to this many rows
-        self.max_rows = ((cap + self.align - 1) // self.align + self.E_loc) * self.align
+        self.S = min(int(cfg.shadow_experts), 2 * K.MAX_WORLD) if self.world > 1 else 0   # shadow slots per rank / layer
+        self.G_tot = self.E_loc + self.S
+        self.max_rows = ((cap + self.align - 1) // self.align + self.G_tot) * self.align
         self.max_tiles = self.max_rows // 128
         H = cfg.hidden
         sym_rows_bytes = self.max_rows * H * 2
         need = (2 * cfg.num_layers + 2) * (sym_rows_bytes + 4096) + K.MAX_WORLD * self.E * 4 + (32 << 20)
+        if self.S:  # parameters, bf16 mirror and gradients of the shards are peer-visible (replica pull / gradient reduce)
+            rec = sum(int(math.prod(shape)) for shape in cfg.seg_shapes().values())
+            need += cfg.num_layers * (self.G_tot * rec * 10 + (1 << 20))
         self.heap = SymmetricHeap(heap_bytes or need, group=group, device=self.device)
         self.flags, self.flags_off = self.heap.alloc((K.NUM_SLOTS, K.MAX_WORLD), torch.int32)
         self.cnt_all, self.cnt_all_off = self.heap.alloc((K.MAX_WORLD, self.E), torch.int32)
@@ -149,29 +163,43 @@ class ExpertShard:
     """Stacked parameters / gradients / Adam state of the E_loc local experts of one layer (flat fp32 buffers, segments
     [E_loc, size] per tensor kind) plus the bf16 mirror consumed by the GEMMs."""
 
-    def __init__(self, cfg: DMoEConfig, E_loc: int, first_expert: int, device, layer_index: int = 0):
+    def __init__(self, cfg: DMoEConfig, E_loc: int, first_expert: int, device, layer_index: int = 0, ctx=None):
         self.cfg, self.E_loc, self.first_expert = cfg, E_loc, first_expert
+        # slots = owned experts + shadow slots (replicas of other ranks' hot experts, only on multi-GPU runs)
+        self.slots = slots = E_loc + (ctx.S if ctx is not None else 0)
         shapes = cfg.seg_shapes()
         self.seg_sizes = [int(math.prod(shapes[n])) for n in SEG_NAMES]
-        total = sum(self.seg_sizes) * E_loc
+        total = sum(self.seg_sizes) * slots
         f32 = dict(dtype=torch.float32, device=device)
-        self.p = torch.empty(total, **f32)
-        self.g = torch.zeros(total, **f32)
+        self.p_off = self.g_off = self.pbf16_off = -1
+        if ctx is not None and ctx.S > 0:   # peer-visible: replicas are pulled from p / p_bf16, partial grads read from g
+            self.p, self.p_off = ctx.heap.alloc((total,), torch.float32)
+            self.g, self.g_off = ctx.heap.alloc((total,), torch.float32)
+            self.p_bf16, self.pbf16_off = ctx.heap.alloc((total,), torch.bfloat16)
+            self.p.zero_(), self.g.zero_(), self.p_bf16.zero_()
+        else:
+            self.p = torch.zeros(total, **f32)
+            self.g = torch.zeros(total, **f32)
+            self.p_bf16 = torch.zeros(total, dtype=torch.bfloat16, device=device)
         self.m = torch.zeros(total, **f32)
         self.v = torch.zeros(total, **f32)
         self.vmax = torch.zeros(total, **f32) if cfg.amsgrad else None
-        self.p_bf16 = torch.empty(total, dtype=torch.bfloat16, device=device)
         self.step = torch.zeros(E_loc, dtype=torch.int32, device=device)
         self.views: Dict[str, torch.Tensor] = {}
         self.grads: Dict[str, torch.Tensor] = {}
         self.bf16: Dict[str, torch.Tensor] = {}
         off = 0
         for name, size in zip(SEG_NAMES, self.seg_sizes):
-            sl = slice(off, off + size * E_loc)
-            self.views[name] = self.p[sl].view(E_loc, *shapes[name])
-            self.grads[name] = self.g[sl].view(E_loc, *shapes[name])
-            self.bf16[name] = self.p_bf16[sl].view(E_loc, *shapes[name])
-            off += size * E_loc
+            sl = slice(off, off + size * slots)
+            self.views[name] = self.p[sl].view(slots, *shapes[name])
+            self.grads[name] = self.g[sl].view(slots, *shapes[name])
+            self.bf16[name] = self.p_bf16[sl].view(slots, *shapes[name])
+            off += size * slots
+        self.w8 = None        # MXFP8 copies of w1/w2/w3 (expert_dtype == "fp8"), refreshed lazily from the bf16 mirror
+        self.w8_dirty = True
+        if cfg.expert_dtype == "fp8" and ctx is not None:
+            self.w8 = {n: fp8.MXFP8Tensor(shapes[n][0], slots, shapes[n][1], fp8.WEIGHT_TILE, device)
+                       for n in ("w1", "w2", "w3")}
         self.reset_parameters(layer_index)
 
     @torch.no_grad()
@@ -193,7 +221,16 @@ class ExpertShard:
                 self.views[bname][le].zero_()
         self.sync_bf16()
 
+    def fp8_weights(self):
+        """MXFP8 weights of all slots, re-quantised from the bf16 mirror when it changed (optimizer step / replica pull)"""
+        if self.w8_dirty:
+            for n, t in self.w8.items():
+                fp8.quantize(self.bf16[n].view(-1, t.K), tile_rows=fp8.WEIGHT_TILE, groups=self.slots, out=t)
+            self.w8_dirty = False
+        return self.w8
+
     def sync_bf16(self):
+        self.w8_dirty = True
         if self.p.is_cuda:
             K.cast_bf16(self.p, self.p_bf16)
         else:
@@ -246,7 +283,7 @@ class ExpertShard:
         for n, size in zip(SEG_NAMES, self.seg_sizes):
             if n == name:
                 return off
-            off += size * self.E_loc
+            off += size * self.slots
         raise KeyError(name)
 
 
@@ -264,14 +301,22 @@ class LayerWorkspace:
         self.yo, self.yo_off = ctx.heap.alloc((R, H), torch.bfloat16)   # expert outputs (peers pull)
         self.h1, self.a1 = torch.empty(R, I, **bf), torch.empty(R, I, **bf)
         self.h2, self.a2 = torch.empty(R, I, **bf), torch.empty(R, I, **bf)
+        self.xq = self.aq = None
+        if cfg.expert_dtype == "fp8":   # MXFP8 operands of the forward GEMMs (aq is shared by a1 and a2)
+            self.xq = fp8.MXFP8Tensor(R, 1, H, fp8.ACT_TILE, dev)
+            self.aq = fp8.MXFP8Tensor(R, 1, I, fp8.ACT_TILE, dev)
         self.mean1, self.rstd1 = torch.empty(R, **f32), torch.empty(R, **f32)
         self.mean2, self.rstd2 = torch.empty(R, **f32), torch.empty(R, **f32)
         P = cfg.tokens_per_rank * cfg.k
         self.idx, self.pos, self.pair_row = torch.empty(P, **i32), torch.empty(P, **i32), torch.empty(P, **i32)
         self.w = torch.empty(P, **f32)
         self.dst_row = torch.empty(ctx.E, **i32)
-        self.group_off = torch.zeros(ctx.E_loc + 1, **i32)
-        self.group_rows = torch.zeros(ctx.E_loc, **i32)
+        self.route_owner = torch.zeros(ctx.E, **i32)            # rank whose buffer holds MY rows of expert e
+        self.group_off = torch.zeros(ctx.G_tot + 1, **i32)      # owned experts, then shadow slots
+        self.group_rows = torch.zeros(ctx.G_tot, **i32)         # rows in MY buffer per group
+        self.step_rows = torch.zeros(ctx.E_loc, **i32)          # global rows per owned expert (optimizer gating, stats)
+        self.shadow_info = torch.full((max(ctx.S, 1) * 4,), -1, **i32)
+        self.owned_shadow = torch.full((ctx.E_loc * 2,), -1, **i32)
         self.tile_group = torch.full((ctx.max_tiles,), -1, **i32)
         self.total_rows = torch.zeros(1, **i32)
 
@@ -318,7 +363,7 @@ class FusedDMoE(nn.Module):
         else:  # CPU / oracle mode: all experts local
             self.E_loc, self.first_expert, dev = cfg.num_experts, 0, device or torch.device("cpu")
             self.ws = None
-        self.shard = ExpertShard(cfg, self.E_loc, self.first_expert, dev, layer_index)
+        self.shard = ExpertShard(cfg, self.E_loc, self.first_expert, dev, layer_index, ctx=ctx)
         self.ref_fail_mask = None  # tests can inject an explicit failure mask into the oracle path
         self._ref_rows = None
 
@@ -354,24 +399,49 @@ class FusedDMoE(nn.Module):
         K.layout_exchange(c.cnt_all_off, c.flags_off, K.SLOT_COUNTS, epoch, c.E, c.E_loc, c.max_rows, align=c.align,
                           counts=c.counts,
                           dst_row=ws.dst_row, group_off=ws.group_off, group_rows=ws.group_rows,
-                          tile_group=ws.tile_group, total_rows=ws.total_rows, status=c.status)
+                          tile_group=ws.tile_group, total_rows=ws.total_rows, status=c.status, shadow_slots=c.S,
+                          shadow_tol=cfg.shadow_tol, min_shadow_rows=cfg.shadow_min_rows, route_owner=ws.route_owner,
+                          step_rows=ws.step_rows, shadow_info=ws.shadow_info, owned_shadow=ws.owned_shadow)
+        if c.S:  # replicas of this step's hot experts: weights from the owners' bf16 mirror, small params from fp32
+            K.pull_shadow(ws.shadow_info, c.S, c.E_loc, sh.p_off, sh.pbf16_off, sh.seg_sizes, SMALL_SEG_MASK)
+            sh.w8_dirty = True
         K.scatter_rows(x, None, idx, pos, ws.dst_row, pair_row, ws.xd_off, c.flags_off, K.SLOT_DISPATCH, epoch, k,
-                       c.E_loc, c.max_rows, ws.group_off, ws.group_rows, c.done_counter, c.status, align=c.align)
+                       c.E_loc, c.max_rows, ws.group_off, ws.group_rows, c.done_counter, c.status, align=c.align,
+                       route_owner=ws.route_owner, num_groups=c.G_tot)
         # ---- expert FFN on the rows this rank received (grouped by expert).  Receive-side fusion: the first GEMM's TMA
         # producer polls the peers' dispatch flags itself (no separate wait kernel)
         tg = ws.tile_group
         wait = (c.flags[K.SLOT_DISPATCH, :c.world], epoch, c.status) if c.world > 1 else None
-        gemm.grouped_linear(ws.xd, sh.bf16["w1"], tile_group=tg, bias=sh.views["b1"], out=ws.h1, two_cta=c.two_cta,
-                            wait=wait)
-        K.ln_relu_fwd(ws.h1, sh.views["g1"], sh.views["be1"], tg, out=ws.a1, mean=ws.mean1, rstd=ws.rstd1)
-        gemm.grouped_linear(ws.a1, sh.bf16["w2"], tile_group=tg, bias=sh.views["b2"], out=ws.h2, two_cta=c.two_cta)
-        K.ln_relu_fwd(ws.h2, sh.views["g2"], sh.views["be2"], tg, out=ws.a2, mean=ws.mean2, rstd=ws.rstd2)
-        gemm.grouped_linear(ws.a2, sh.bf16["w3"], tile_group=tg, bias=sh.views["b3"], residual=ws.xd, out=ws.yo,
-                            two_cta=c.two_cta)
+        if cfg.expert_dtype == "fp8":
+            self._expert_ffn_fp8(wait, epoch)
+        else:
+            gemm.grouped_linear(ws.xd, sh.bf16["w1"], tile_group=tg, bias=sh.views["b1"], out=ws.h1, two_cta=c.two_cta,
+                                wait=wait)
+            K.ln_relu_fwd(ws.h1, sh.views["g1"], sh.views["be1"], tg, out=ws.a1, mean=ws.mean1, rstd=ws.rstd1)
+            gemm.grouped_linear(ws.a1, sh.bf16["w2"], tile_group=tg, bias=sh.views["b2"], out=ws.h2, two_cta=c.two_cta)
+            K.ln_relu_fwd(ws.h2, sh.views["g2"], sh.views["be2"], tg, out=ws.a2, mean=ws.mean2, rstd=ws.rstd2)
+            gemm.grouped_linear(ws.a2, sh.bf16["w3"], tile_group=tg, bias=sh.views["b3"], residual=ws.xd, out=ws.yo,
+                                two_cta=c.two_cta)
         y = torch.empty(B, cfg.hidden, dtype=torch.bfloat16, device=x.device)
         K.combine_rows(ws.yo_off, idx, pair_row, w, y, k, c.E_loc, flags_off=c.flags_off, slot=K.SLOT_OUTPUT, epoch=epoch,
-                       signal=c.world > 1, wait=c.world > 1, status=c.status)
+                       signal=c.world > 1, wait=c.world > 1, status=c.status, route_owner=ws.route_owner)
         return y
+
+    def _expert_ffn_fp8(self, wait, epoch):
+        """forward GEMMs on block-scaled FP8 tensor cores; LayerNorm emits the next GEMM's MXFP8 operand directly (and the
+        bf16 copy the bf16 wgrad needs)"""
+        c, ws, sh = self.ctx, self.ws, self.shard
+        assert c.two_cta, "the FP8 GEMM is a CTA-pair kernel (hidden and 4*hidden must be multiples of 256)"
+        tg = ws.tile_group
+        if wait is not None:  # the quantiser is the first consumer of the rows pushed by the peers
+            K.signal_wait(c.flags_off, K.SLOT_DISPATCH, epoch, c.status, signal=False, wait=True)
+        w8 = sh.fp8_weights()
+        fp8.quantize(ws.xd, tile_group=tg, out=ws.xq)
+        fp8.grouped_linear_fp8(ws.xq, w8["w1"], tile_group=tg, bias=sh.views["b1"], out=ws.h1)
+        K.ln_relu_fwd(ws.h1, sh.views["g1"], sh.views["be1"], tg, out=ws.a1, mean=ws.mean1, rstd=ws.rstd1, quant=ws.aq)
+        fp8.grouped_linear_fp8(ws.aq, w8["w2"], tile_group=tg, bias=sh.views["b2"], out=ws.h2)
+        K.ln_relu_fwd(ws.h2, sh.views["g2"], sh.views["be2"], tg, out=ws.a2, mean=ws.mean2, rstd=ws.rstd2, quant=ws.aq)
+        fp8.grouped_linear_fp8(ws.aq, w8["w3"], tile_group=tg, bias=sh.views["b3"], residual=ws.xd, out=ws.yo)
 
     def _backward_cuda(self, gy, B):
         c, ws, sh, cfg = self.ctx, self.ws, self.shard, self.cfg
@@ -381,12 +451,15 @@ class FusedDMoE(nn.Module):
         idx, w, pos, pair_row = ws.idx[:P], ws.w[:P], ws.pos[:P], ws.pair_row[:P]
         gy = gy.to(torch.bfloat16)
         dlogits = torch.empty(B, sum(self.grid_size), dtype=torch.float32, device=gy.device)
-        K.gate_bwd(ws.yo_off, gy, idx, pair_row, w, dlogits, k, c.E_loc, self.grid_size)
+        K.gate_bwd(ws.yo_off, gy, idx, pair_row, w, dlogits, k, c.E_loc, self.grid_size, route_owner=ws.route_owner)
         K.scatter_rows(gy, w, idx, pos, None, pair_row, c.gyd_off, c.flags_off, K.SLOT_GRAD, epoch, k, c.E_loc,
-                       c.max_rows, ws.group_off, ws.group_rows, c.done_counter, c.status, align=c.align)
+                       c.max_rows, ws.group_off, ws.group_rows, c.done_counter, c.status, align=c.align,
+                       route_owner=ws.route_owner, num_groups=c.G_tot)
+        if c.S:  # atomically accumulated (bias / LayerNorm) partial gradients of my shadow slots start from zero
+            K.zero_slots(sh.g, sh.seg_sizes, c.G_tot, c.E_loc, c.S, SMALL_SEG_MASK)
         if c.world > 1:  # the first consumers of the pushed gradients are the colsum / wgrad kernels
             K.signal_wait(c.flags_off, K.SLOT_GRAD, epoch, c.status, signal=False, wait=True)
-        tg, go, G = ws.tile_group, ws.group_off, c.E_loc
+        tg, go, G = ws.tile_group, ws.group_off, c.G_tot
         gr = sh.grads
         K.grouped_colsum(c.gyd, tg, out=gr["b3"])
         gemm.grouped_wgrad(c.gyd, ws.a2, go, G, out=gr["w3"], two_cta=c.two_cta)
@@ -401,18 +474,23 @@ class FusedDMoE(nn.Module):
         gemm.grouped_linear(c.dh, sh.bf16["w1"], tile_group=tg, w_is_kn=True, residual=c.gyd, out=c.dxd,
                             two_cta=c.two_cta)
         # ---- expert-side optimizer step (reference: ExpertBackend.apply_gradients right after backward)
+        if c.S:  # the owners read every rank's partial gradients of the shadowed experts: all ranks must be done
+            K.signal_wait(c.flags_off, K.SLOT_SHADOW, epoch, c.status, signal=True, wait=True)
         self.apply_expert_gradients()
         dx = torch.empty(B, cfg.hidden, dtype=torch.bfloat16, device=gy.device)
         K.combine_rows(c.dxd_off, idx, pair_row, None, dx, k, c.E_loc, flags_off=c.flags_off, slot=K.SLOT_DINPUT,
-                       epoch=epoch, signal=c.world > 1, wait=c.world > 1, status=c.status)
+                       epoch=epoch, signal=c.world > 1, wait=c.world > 1, status=c.status, route_owner=ws.route_owner)
         return dx, dlogits
 
     def apply_expert_gradients(self):
-        sh, cfg, ws = self.shard, self.cfg, self.ws
-        K.bump_steps(sh.step, ws.group_rows)
-        K.adam_step(sh.p, sh.g, sh.m, sh.v, sh.vmax, sh.p_bf16, sh.seg_sizes, self.E_loc, step=sh.step,
-                    group_rows=ws.group_rows, lr=cfg.lr, betas=cfg.betas, eps=cfg.eps, amsgrad=cfg.amsgrad,
-                    zero_mask=SMALL_SEG_MASK)
+        sh, cfg, ws, c = self.shard, self.cfg, self.ws, self.ctx
+        K.bump_steps(sh.step, ws.step_rows)
+        K.adam_step(sh.p, sh.g, sh.m, sh.v, sh.vmax, sh.p_bf16, sh.seg_sizes, sh.slots, step=sh.step,
+                    group_rows=ws.step_rows, lr=cfg.lr, betas=cfg.betas, eps=cfg.eps, amsgrad=cfg.amsgrad,
+                    zero_mask=SMALL_SEG_MASK, G_active=self.E_loc, world=c.world,
+                    peer_bases=c.heap.peer_bases if c.S else None, shadow_of=ws.owned_shadow if c.S else None,
+                    shadow_g_off=sh.g_off, me=c.rank)
+        sh.w8_dirty = True
 
     def failure_rate_ref(self) -> float:
         return self.cfg.failure_rate if (self.training and self.ctx is None) else 0.0
@@ -427,7 +505,7 @@ class FusedDMoE(nn.Module):
             for n, size in zip(SEG_NAMES, sh.seg_sizes):
                 shape = sh.views[n].shape[1:]
                 out[n] = sh.p[off + e_local * size: off + (e_local + 1) * size].view(shape)
-                off += size * sh.E_loc
+                off += size * sh.slots
             return out
         return {n: self.shard.views[n][e_local].to(dtype) for n in SEG_NAMES}
 

@@ -48,7 +48,7 @@ def layer_check():
     return gpu_layer_check
 
 
-@pytest.mark.parametrize("check", ["check_gate", "check_ln", "check_adam", "check_layer"])
+@pytest.mark.parametrize("check", ["check_gate", "check_ln", "check_adam", "check_layer", "check_layer_fp8"])
 def test_kernels_and_fused_layer_against_oracles(layer_check, check):
     layer_check.results.clear()
     getattr(layer_check, check)()
@@ -94,9 +94,33 @@ def test_fused_trainer_matches_baseline_trainer_one_step():
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_two_gpu_p2p_dispatch_matches_single_gpu():
+@pytest.mark.parametrize("extra", [[], ["--force-shadow"]])
+def test_two_gpu_p2p_dispatch_matches_single_gpu(extra):
+    """fused P2P engine on 2 GPUs == single-process oracle; with --force-shadow the hot-expert replica path (weights pulled
+    over NVLink, partial weight gradients reduced inside the owner's Adam kernel) is exercised for 4 experts"""
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
                           "--master-addr", "127.0.0.1", "--master-port", "29541",
-                          os.path.join(ROOT, "tools", "multi_gpu_check.py")], capture_output=True, text=True, timeout=600)
+                          os.path.join(ROOT, "tools", "multi_gpu_check.py"), *extra], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "MULTI_GPU_OK" in out.stdout, out.stdout[-3000:]
+
+
+@pytest.mark.parametrize("check", ["check_attention", "check_layer"])
+def test_attention_kernel_and_native_transformer_expert(check):
+    """tcgen05 attention (csrc/attention.cu) and the sm_100a transformer expert vs fp32 PyTorch oracles"""
+    from tools import gpu_attention_check as A
+    A.results.clear()
+    getattr(A, check)()
+    bad = {k: v for k, v in A.results.items() if not v.get("ok")}
+    assert A.results and not bad, bad
+
+
+@pytest.mark.parametrize("check", ["check_quant", "check_gemm"])
+def test_mxfp8_quantiser_and_block_scaled_gemm(check):
+    """MXFP8 quantisation kernel == PyTorch oracle bit for bit; tcgen05 kind::mxf8f6f4.block_scale grouped GEMM == fp32
+    matmul of the dequantised operands"""
+    from tools import gpu_fp8_check as Q
+    Q.results.clear()
+    getattr(Q, check)()
+    bad = {k: v for k, v in Q.results.items() if not v.get("ok")}
+    assert Q.results and not bad, bad

@@ -23,7 +23,9 @@ def main():
     torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
     dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
     B = 256
-    cfg = E.DMoEConfig(hidden=512, grid_size=(4, 4), k=4, num_layers=1, tokens_per_rank=B, capacity_factor=4.0)
+    force_shadow = "--force-shadow" in sys.argv  # shadow as many experts as there are slots (exercises the replica path)
+    cfg = E.DMoEConfig(hidden=512, grid_size=(4, 4), k=4, num_layers=1, tokens_per_rank=B, capacity_factor=4.0,
+                       shadow_experts=4, shadow_tol=0.0 if force_shadow else 1.1, shadow_min_rows=1 if force_shadow else 64)
     ctx = E.EngineContext(cfg)
     torch.manual_seed(0)  # identical gate on every rank (DMoETrainer does the same)
     layer = E.FusedDMoE(cfg, ctx).cuda()
@@ -35,6 +37,7 @@ def main():
     y.backward(g_all[rank * B: (rank + 1) * B].cuda())
     torch.cuda.synchronize()
     ctx.check_status()
+    shadowed = int((layer.ws.shadow_info.view(-1, 4)[:, 0] >= 0).sum())
     # gather what the distributed run produced
     ys = [torch.empty_like(y) for _ in range(world)]
     dxs = [torch.empty_like(x.grad) for _ in range(world)]
@@ -42,9 +45,12 @@ def main():
     dist.all_gather(dxs, x.grad.contiguous())
     gw = layer.proj.weight.grad.clone()
     dist.all_reduce(gw)
-    w1 = layer.shard.views["w1"].clone()
+    w1 = layer.shard.views["w1"][:layer.E_loc].clone()
     w1s = [torch.empty_like(w1) for _ in range(world)]
     dist.all_gather(w1s, w1)
+    b2 = layer.shard.views["b2"][:layer.E_loc].clone()
+    b2s = [torch.empty_like(b2) for _ in range(world)]
+    dist.all_gather(b2s, b2)
     steps = [torch.empty_like(layer.shard.step) for _ in range(world)]
     dist.all_gather(steps, layer.shard.step)
     ok = True
@@ -61,9 +67,11 @@ def main():
         ref.apply_expert_gradients_ref()
         errs = dict(y=rel(torch.cat(ys), yr), dx=rel(torch.cat(dxs), xr.grad), dproj=rel(gw, ref.proj.weight.grad),
                     w1_mean_abs=(torch.cat(w1s) - ref.shard.views["w1"]).abs().mean().item(),
+                    b2_max_abs=(torch.cat(b2s) - ref.shard.views["b2"]).abs().max().item(),
                     steps=bool((torch.cat(steps).cpu() == ref.shard.step.cpu()).all()))
-        ok = errs["y"] < 2e-2 and errs["dx"] < 3e-2 and errs["dproj"] < 5e-2 and errs["w1_mean_abs"] < 1e-4 and errs["steps"]
-        print("multi_gpu_check", errs, flush=True)
+        ok = errs["y"] < 2e-2 and errs["dx"] < 3e-2 and errs["dproj"] < 5e-2 and errs["w1_mean_abs"] < 1e-4 and errs["b2_max_abs"] < 2.5e-3 and errs["steps"]
+        ok = ok and (shadowed > 0 or not force_shadow)
+        print("multi_gpu_check", dict(force_shadow=force_shadow, shadowed_experts=shadowed), errs, flush=True)
         print("MULTI_GPU_OK" if ok else "MULTI_GPU_FAILED", flush=True)
     dist.barrier()
     dist.destroy_process_group()
