@@ -44,6 +44,10 @@ def parse_args():
     ap.add_argument("--failure-rate", type=float, default=0.0)
     ap.add_argument("--capacity-factor", type=float, default=0.0,
                     help="receive-buffer rows / local (token, expert) pairs; 0 = auto (retry with a larger one on overflow)")
+    ap.add_argument("--shadow-experts", type=int, default=8,
+                    help="max hot experts per layer and step that are processed data-parallel on every rank (0 = static placement)")
+    ap.add_argument("--expert-dtype", choices=["bf16", "fp8"], default="bf16",
+                    help="fp8 = forward expert GEMMs on block-scaled FP8 tensor cores (MXFP8)")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
 
@@ -165,6 +169,8 @@ def run_ours(args):
         factors = [args.capacity_factor]
     elif os.environ.get("LAH_BENCH_FACTORS"):
         factors = [float(f) for f in os.environ["LAH_BENCH_FACTORS"].split(",")]
+    elif args.shadow_experts > 0 and world > 1:   # balanced by shadowing: every rank receives ~ its own share
+        factors = sorted({1.5, min(2.5, float(world)), float(world)})
     else:
         factors = sorted({min(3.0, float(world)), min(5.0, float(world)), float(world)})
     for attempt, factor in enumerate(factors):
@@ -193,7 +199,7 @@ def _measure_ours(args, rank, world, local_rank, B, capacity_factor):
     from lah_b200.parallel.trainer import DMoETrainer
     cfg = DMoEConfig(hidden=args.hidden, grid_size=tuple(args.grid), k=args.k, num_layers=args.layers,
                      tokens_per_rank=B, capacity_factor=capacity_factor, failure_rate=args.failure_rate,
-                     gate_mode=args.gate)
+                     gate_mode=args.gate, shadow_experts=args.shadow_experts, expert_dtype=args.expert_dtype)
     trainer = DMoETrainer(cfg)
     gen = torch.Generator().manual_seed(1234 + rank)
     n_batches = 4
@@ -230,6 +236,7 @@ def _measure_ours(args, rank, world, local_rank, B, capacity_factor):
     sampler = ClockSampler(local_rank)
     sampler.start()
     native.reset_launches()
+    trainer.ctx.exposed_wait_ms(reset=True)
     profiling = bool(os.environ.get("LAH_CUDA_PROFILE"))  # ncu --profile-from-start off
     if profiling:
         torch.cuda.profiler.start()
@@ -237,6 +244,7 @@ def _measure_ours(args, rank, world, local_rank, B, capacity_factor):
     if profiling:
         torch.cuda.profiler.stop()
     launches = native.launches()
+    exposed_ms = max_over_ranks(trainer.ctx.exposed_wait_ms(reset=True) / args.steps, world)
     clocks = sampler.stop()
     check_all_ranks()
     global_batch = B * world
@@ -257,7 +265,8 @@ def _measure_ours(args, rank, world, local_rank, B, capacity_factor):
     for block in trainer.model.blocks:  # tokens-per-expert histogram of the last step (observability)
         rows = block.ws.step_rows.float()
         routing.append({"active_experts": int((rows > 0).sum()), "max_rows": int(rows.max()), "mean_rows": float(rows.mean()),
-                        "padded_rows": int(block.ws.total_rows.item())})
+                        "padded_rows": int(block.ws.total_rows.item()),
+                        "shadowed_experts": int((block.ws.shadow_info.view(-1, 4)[:, 0] >= 0).sum())})
     if rank == 0:
         out = {
             "metric": "DMoE training samples/sec (whole job, device-timed, max over ranks)",
@@ -268,11 +277,13 @@ def _measure_ours(args, rank, world, local_rank, B, capacity_factor):
                                 f"FeedforwardBlock({cfg.hidden}), top-{cfg.k}] -> LayerNorm -> Linear({cfg.hidden},10); "
                                 "fwd+bwd+per-expert AMSGrad+trainer AMSGrad",
                        "global_batch": global_batch, "seq_len": 1, "parallelism": f"ep{world}+dp{world}",
-                       "capacity_factor": capacity_factor,
+                       "capacity_factor": capacity_factor, "shadow_experts": cfg.shadow_experts if world > 1 else 0,
+                       "expert_gemm_dtype": cfg.expert_dtype + (" forward, bf16 dgrad/wgrad" if cfg.expert_dtype == "fp8" else ""),
                        "experts_total": cfg.num_experts * cfg.num_layers, "failure_rate": cfg.failure_rate,
                        "gate": cfg.gate_mode + (" (LayerNorm(x) @ normalize(keys); gate params not trained, exactly like the reference's EmulatedDMoE)" if cfg.gate_mode == "emulator" else " (trainable product-key proj, lib.GatingFunction)"),
                        "l2_policy": "working set per step (>35 GB of expert state + >10 GB activations) exceeds the 126 MB L2; no explicit flush"},
             "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "routing_rank0": routing,
+            "exposed_comm_wait_ms_per_step": exposed_ms,
             "baseline_note": "vs_baseline = value / 16.8 samples/s (reference notebook dmoe64x4, BASELINE.md)",
         }
         print(json.dumps(out))

@@ -30,6 +30,7 @@ struct Peers {
     char* base[MAX_WORLD];  // base of every rank's symmetric heap, as mapped in THIS process
     int world;
     int me;
+    unsigned long long* wait_ns;  // optional device counter: ns this rank spent blocked on peer flags ("exposed" comm)
 };
 
 struct GridSpec {
@@ -60,6 +61,14 @@ __device__ __forceinline__ bool spin_until_ge(const int* flag, int epoch, int* s
         }
     }
     return true;
+}
+
+// called by the threads [0, world) of one warp right after their spin: adds the LONGEST of their waits to the counter
+__device__ __forceinline__ void account_wait(const Peers& peers, unsigned long long t0, int world) {
+    const unsigned long long dt64 = globaltimer_ns() - t0;
+    const unsigned mask = (world >= 32) ? 0xffffffffu : ((1u << world) - 1u);
+    const unsigned dt = __reduce_max_sync(mask, dt64 > 0xffffffffull ? 0xffffffffu : static_cast<unsigned>(dt64));
+    if (peers.wait_ns && (threadIdx.x & 31) == 0) atomicAdd(peers.wait_ns, static_cast<unsigned long long>(dt));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -243,7 +252,9 @@ __global__ void __launch_bounds__(1024) layout_exchange_kernel(Peers peers, Layo
         st_release_sys(f, a.epoch);
         // 2. wait for everybody's counts
         const int* fw = reinterpret_cast<const int*>(peers.base[me] + a.flags_off) + a.slot * MAX_WORLD + tid;
+        const unsigned long long t0 = globaltimer_ns();
         spin_until_ge(fw, a.epoch, a.status);
+        account_wait(peers, t0, world);
     }
     for (int t = tid; t < a.max_tiles; t += blockDim.x) a.tile_group[t] = -1;
     if (tid < MAX_WORLD) s_load[tid] = 0;
@@ -549,7 +560,9 @@ __global__ void signal_wait_kernel(Peers peers, long long flags_off, int slot, i
     }
     if (do_wait && lane < peers.world) {
         const int* f = reinterpret_cast<const int*>(peers.base[peers.me] + flags_off) + slot * MAX_WORLD + lane;
+        const unsigned long long t0 = globaltimer_ns();
         spin_until_ge(f, epoch, status);
+        account_wait(peers, t0, peers.world);
     }
 }
 
@@ -582,7 +595,9 @@ __global__ void __launch_bounds__(256) combine_rows_kernel(Peers peers, CombineA
     if (a.do_wait) {
         if (threadIdx.x < peers.world) {
             const int* f = reinterpret_cast<const int*>(peers.base[peers.me] + a.flags_off) + a.slot * MAX_WORLD + threadIdx.x;
+            const unsigned long long t0 = globaltimer_ns();
             spin_until_ge(f, a.epoch, a.status);
+            if (blockIdx.x == 0) account_wait(peers, t0, peers.world);
         }
         __syncthreads();
     }
@@ -774,7 +789,14 @@ int lah_set_peers(const unsigned long long* bases, int world, int me) {
     for (int i = 0; i < MAX_WORLD; ++i) g_peers.base[i] = i < world ? reinterpret_cast<char*>(bases[i]) : nullptr;
     g_peers.world = world;
     g_peers.me = me;
+    g_peers.wait_ns = nullptr;
     g_peers_set = true;
+    return 0;
+}
+
+// device counter (8 bytes) that accumulates the ns this rank spends blocked on peer flags; NULL disables
+int lah_set_wait_counter(unsigned long long* counter) {
+    g_peers.wait_ns = counter;
     return 0;
 }
 

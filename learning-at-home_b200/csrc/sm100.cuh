@@ -292,6 +292,11 @@ __device__ __forceinline__ bool spin_flag_ge(const int* flag, int epoch) {
     }
     return true;
 }
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 // order generic-proxy observations (the acquire above) before subsequent async-proxy (TMA) reads of global memory
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 

@@ -31,6 +31,7 @@ def _lib():
         "lah_ln_relu_bwd": [P, P, P, P, P, P, P, P, P, P, P, I, I, I, P],
         "lah_grouped_colsum": [P, L, P, I, P, I, P],
         "lah_set_peers": [P, I, I],
+        "lah_set_wait_counter": [P],
         "lah_gate_topk": [P, I, P, I, I, P, Fl, c_ull, L, P, P, P, P, P],
         "lah_layout_exchange": [L, L, I, I, I, I, I, I, P, P, P, P, P, P, P, I, Fl, I, P, P, P, P, P],
         "lah_scatter_rows": [P, P, P, P, P, P, L, L, I, I, I, I, I, I, I, I, P, P, P, P, P, I, P],
@@ -106,6 +107,11 @@ def grouped_colsum(x, tile_group, *, out):
 def set_peers(bases, me):
     arr = (c_ull * len(bases))(*[int(b) for b in bases])
     native.check(_lib().lah_set_peers(ctypes.cast(arr, c_void_p), len(bases), me), "lah_set_peers")
+
+
+def set_wait_counter(counter):
+    """int64 device tensor [1] accumulating the ns this rank spends blocked on peer flags (None disables)"""
+    native.check(_lib().lah_set_wait_counter(ptr(counter)), "lah_set_wait_counter")
 
 
 def gate_topk(logits, grid_size, k, *, alive=None, failure_rate=0.0, seed=0, token_offset=0, idx, w, pos, counts):

@@ -131,7 +131,12 @@ class EngineContext:
         i32 = dict(dtype=torch.int32, device=self.device)
         self.counts = torch.zeros(self.E, **i32)
         self.done_counter = torch.zeros(1, **i32)
-        self.status = torch.zeros(1, **i32)
+        # [0] status bits; [2:4] = 64-bit counter of ns spent blocked on peer flags ("exposed" communication), written by
+        # the wait loops of csrc/moe.cu (through lah_set_wait_counter) and by the receive-side wait fused into the GEMMs
+        self._status_buf = torch.zeros(4, **i32)
+        self.status = self._status_buf[:1]
+        self.wait_ns = self._status_buf[2:4].view(torch.int64)
+        K.set_wait_counter(self.wait_ns)
         self.alive = torch.ones(self.E, dtype=torch.uint8, device=self.device)
         self.epoch = 0
         self.token_counter = 0
@@ -146,6 +151,13 @@ class EngineContext:
     def next_epoch(self) -> int:
         self.epoch += 1
         return self.epoch
+
+    def exposed_wait_ms(self, reset: bool = True) -> float:
+        """ms this rank's stream was blocked on peer flags since the last reset (synchronises)"""
+        ms = float(self.wait_ns.item()) * 1e-6
+        if reset:
+            self.wait_ns.zero_()
+        return ms
 
     def check_status(self):
         """host-side check of the device status word (synchronises); raises on timeouts / capacity overflow"""

@@ -194,3 +194,20 @@ def test_baseline_all_to_all_two_processes_matches_single_process():
     assert results[0] == pytest.approx(results[1], abs=1e-6)
     # first step is identical; later steps differ only because the sharded experts see rows from both ranks
     assert results[0][0] == pytest.approx(ref[0], abs=1e-5)
+
+
+def test_mxfp8_reference_quantiser_roundtrip():
+    """MXFP8 oracle (ops/fp8.py): power-of-two block scales never saturate E4M3 and the relative error is bounded"""
+    from lah_b200.ops import fp8
+    torch.manual_seed(0)
+    x = torch.randn(64, 256) * torch.logspace(-3, 3, 64).unsqueeze(1)
+    x[3] = 0
+    q, e = fp8.quantize_ref(x)
+    assert q.dtype == torch.float8_e4m3fn and e.shape == (64, 8)
+    assert float(q.float().abs().max()) <= 448.0
+    back = fp8.dequantize_ref(q, e)
+    blk_amax = x.view(64, 8, 32).abs().amax(-1, keepdim=True).expand(64, 8, 32).reshape(64, 256)
+    assert bool(((back - x).abs() <= blk_amax * 2 ** -3 + 1e-30).all())   # <= 1/2 ulp of a 3-bit mantissa, block-relative
+    assert bool((back[3] == 0).all())
+    assert fp8.sf_bytes(2048, 3, 512, fp8.WEIGHT_TILE) == 11 * 4 * 2 * 3 * 512
+    assert fp8.sf_bytes(384, 1, 512, fp8.ACT_TILE) == 3 * 4 * 512
