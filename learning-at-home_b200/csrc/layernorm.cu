@@ -7,116 +7,146 @@
 // Rows are grouped by expert in 128-row tiles; tile_group[t] gives the expert (or -1: tile unused, skipped).
 #include "sm100.cuh"
 #include <cuda_fp8.h>
+#include <stdlib.h>
 
 namespace lah {
 
 constexpr float LN_EPS = 1e-5f;
 
 // ------------------------------------------------------------------------------------------------
-// forward: one warp per row, lane owns C/32 columns as chunks of 8 (coalesced 16B accesses)
+// forward: one warp per R consecutive rows (same 128-row tile => same expert), lane owns C/32 columns as chunks of 8
+// (coalesced 16B accesses)
 //   a = relu((h - mean) * rstd * gamma + beta);  saves mean / rstd per row
+// Why R rows per warp: gamma / beta are 2 x 4 B per column against 2 B of payload, i.e. with one row per warp 2/3 of
+// the bytes through the L1/LSU pipe were affine parameters (ncu: 3.4 TB/s DRAM, L1 the limiter); holding a parameter
+// chunk in registers and applying it to R rows divides that traffic by R.
 // ------------------------------------------------------------------------------------------------
 // With QUANT the kernel ALSO emits the MXFP8 operand of the next expert GEMM (csrc/grouped_gemm_fp8.cu): E4M3 payload +
 // one UE8M0 scale per 32 columns (4 adjacent lanes share a block: two shuffles), quantised from the fp32 value before it
 // is rounded to bf16.  The bf16 copy is optional (a == nullptr in forward-only runs).
-template <int C, bool QUANT>
-__global__ void __launch_bounds__(256, (C <= 2048) ? 3 : 1) ln_relu_fwd_kernel(
+template <int C>
+struct LnFwdCfg {
+    static constexpr int R = (C >= 4096) ? 1 : ((C >= 2048) ? 2 : 4);   // rows per warp (64 packed registers)
+};
+
+static int ln_rows_per_warp(int dflt) {   // LAH_LN_ROWS=1 selects the one-row-per-warp variant (A/B measurements)
+    static int forced = -1;
+    if (forced < 0) {
+        const char* e = getenv("LAH_LN_ROWS");
+        forced = e ? atoi(e) : 0;
+    }
+    return forced == 1 ? 1 : dflt;
+}
+
+template <int C, bool QUANT, int R>
+__global__ void __launch_bounds__(256, 2) ln_relu_fwd_kernel(
     const bf16* __restrict__ h, bf16* __restrict__ a, float* __restrict__ mean_out, float* __restrict__ rstd_out,
     const float* __restrict__ gamma, const float* __restrict__ beta, const int* __restrict__ tile_group, int rows,
     int relu, uint8_t* __restrict__ aq, uint8_t* __restrict__ sf) {
     constexpr int NV = C / 256;  // int4 (8 x bf16) chunks per lane
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int row = blockIdx.x * 8 + warp;
-    if (row >= rows) return;
-    const int g = tile_group ? __ldg(tile_group + (row >> 7)) : 0;
+    const int row0 = (blockIdx.x * 8 + warp) * R;
+    if (row0 >= rows) return;
+    const int g = tile_group ? __ldg(tile_group + (row0 >> 7)) : 0;
     if (g < 0) return;
-    const int4* hp = reinterpret_cast<const int4*>(h + static_cast<long long>(row) * C);
-    // the row stays PACKED (bf16x2) in registers: 4 regs per 8 values instead of 8 -> more resident warps, i.e. more
-    // bytes in flight per SM for this purely bandwidth-bound kernel; values are unpacked on the fly in each pass
-    int4 q[NV];
+    // rows stay PACKED (bf16x2) in registers: 4 regs per 8 values; values are unpacked on the fly in each pass
+    int4 q[R][NV];
 #pragma unroll
-    for (int j = 0; j < NV; ++j) q[j] = ld_nc_v4(hp + j * 32 + lane);
-    float s = 0.f;
+    for (int r = 0; r < R; ++r) {
+        const int4* hp = reinterpret_cast<const int4*>(h + static_cast<long long>(min(row0 + r, rows - 1)) * C);
 #pragma unroll
-    for (int j = 0; j < NV; ++j) {
-        const uint32_t w[4] = {(uint32_t)q[j].x, (uint32_t)q[j].y, (uint32_t)q[j].z, (uint32_t)q[j].w};
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            const float2 f = unpack_bf16x2(w[t]);
-            s += f.x + f.y;
-        }
+        for (int j = 0; j < NV; ++j) q[r][j] = ld_nc_v4(hp + j * 32 + lane);
     }
-    const float mean = warp_sum(s) * (1.f / C);
-    float ss = 0.f;
+    float mean[R], rstd[R];
 #pragma unroll
-    for (int j = 0; j < NV; ++j) {
-        const uint32_t w[4] = {(uint32_t)q[j].x, (uint32_t)q[j].y, (uint32_t)q[j].z, (uint32_t)q[j].w};
+    for (int r = 0; r < R; ++r) {
+        // one pass: sum and sum of squares in fp32 (inputs are bf16: 8 mantissa bits, C <= 4096 -> ample head-room)
+        float s = 0.f, ss = 0.f;
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            const float2 f = unpack_bf16x2(w[t]);
-            const float d0 = f.x - mean, d1 = f.y - mean;
-            ss += d0 * d0 + d1 * d1;
+        for (int j = 0; j < NV; ++j) {
+            const uint32_t w[4] = {(uint32_t)q[r][j].x, (uint32_t)q[r][j].y, (uint32_t)q[r][j].z, (uint32_t)q[r][j].w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const float2 f = unpack_bf16x2(w[t]);
+                s += f.x + f.y;
+                ss += f.x * f.x + f.y * f.y;
+            }
         }
-    }
-    const float rstd = rsqrtf(warp_sum(ss) * (1.f / C) + LN_EPS);
-    if (lane == 0 && mean_out) {
-        mean_out[row] = mean;
-        rstd_out[row] = rstd;
+        s = warp_sum(s);
+        ss = warp_sum(ss);
+        mean[r] = s * (1.f / C);
+        rstd[r] = rsqrtf(fmaxf(ss * (1.f / C) - mean[r] * mean[r], 0.f) + LN_EPS);
+        if (lane == 0 && mean_out && row0 + r < rows) {
+            mean_out[row0 + r] = mean[r];
+            rstd_out[row0 + r] = rstd[r];
+        }
     }
     const float* gp = gamma + static_cast<long long>(g) * C;
     const float* bp = beta + static_cast<long long>(g) * C;
-    int4* ap = reinterpret_cast<int4*>(a + static_cast<long long>(row) * C);
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
         const int col = (j * 32 + lane) * 8;
-        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gp + col));
-        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gp + col + 4));
-        const float4 b0 = __ldg(reinterpret_cast<const float4*>(bp + col));
-        const float4 b1 = __ldg(reinterpret_cast<const float4*>(bp + col + 4));
-        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-        const uint32_t w[4] = {(uint32_t)q[j].x, (uint32_t)q[j].y, (uint32_t)q[j].z, (uint32_t)q[j].w};
-        float y[8];
+        // volatile asm loads: ordered with the volatile asm stores below, so the compiler cannot hoist the parameter
+        // loads of all later chunks to the top (16 registers per chunk -> spills)
+        const int4 g0 = ld_nc_v4(reinterpret_cast<const int4*>(gp + col));
+        const int4 g1 = ld_nc_v4(reinterpret_cast<const int4*>(gp + col + 4));
+        const int4 b0 = ld_nc_v4(reinterpret_cast<const int4*>(bp + col));
+        const int4 b1 = ld_nc_v4(reinterpret_cast<const int4*>(bp + col + 4));
+        const float gg[8] = {__int_as_float(g0.x), __int_as_float(g0.y), __int_as_float(g0.z), __int_as_float(g0.w),
+                             __int_as_float(g1.x), __int_as_float(g1.y), __int_as_float(g1.z), __int_as_float(g1.w)};
+        const float bb[8] = {__int_as_float(b0.x), __int_as_float(b0.y), __int_as_float(b0.z), __int_as_float(b0.w),
+                             __int_as_float(b1.x), __int_as_float(b1.y), __int_as_float(b1.z), __int_as_float(b1.w)};
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            const float2 f = unpack_bf16x2(w[t]);
-            y[2 * t] = (f.x - mean) * rstd * gg[2 * t] + bb[2 * t];
-            y[2 * t + 1] = (f.y - mean) * rstd * gg[2 * t + 1] + bb[2 * t + 1];
-        }
-        if (relu) {
+        for (int r = 0; r < R; ++r) {
+            const int row = row0 + r;
+            if (row >= rows) continue;   // warp-uniform
+            const uint32_t w[4] = {(uint32_t)q[r][j].x, (uint32_t)q[r][j].y, (uint32_t)q[r][j].z, (uint32_t)q[r][j].w};
+            float y[8];
 #pragma unroll
-            for (int t = 0; t < 8; ++t) y[t] = fmaxf(y[t], 0.f);
-        }
-        if (!QUANT || a) {
-            int4 o;
-            o.x = pack_bf16x2(y[0], y[1]);
-            o.y = pack_bf16x2(y[2], y[3]);
-            o.z = pack_bf16x2(y[4], y[5]);
-            o.w = pack_bf16x2(y[6], y[7]);
-            ap[j * 32 + lane] = o;
-        }
-        if (QUANT) {
-            float amax = 0.f;
+            for (int t = 0; t < 4; ++t) {
+                const float2 f = unpack_bf16x2(w[t]);
+                y[2 * t] = (f.x - mean[r]) * rstd[r] * gg[2 * t] + bb[2 * t];
+                y[2 * t + 1] = (f.y - mean[r]) * rstd[r] * gg[2 * t + 1] + bb[2 * t + 1];
+            }
+            if (relu) {
 #pragma unroll
-            for (int t = 0; t < 8; ++t) amax = fmaxf(amax, fabsf(y[t]));
-            amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
-            amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
-            // smallest power-of-two scale with amax / scale <= 448 (same rule as quant_mxfp8_kernel)
-            const uint32_t bits = __float_as_uint(amax * (1.f / 448.f));
-            uint32_t e = ((bits >> 23) & 0xFFu) + ((bits & 0x7FFFFFu) ? 1u : 0u);
-            e = min(max(e, 1u), 253u);
-            const float inv = __uint_as_float((254u - e) << 23);
-            uint2 o8;
-            o8.x = static_cast<uint32_t>(__nv_cvt_float2_to_fp8x2(make_float2(y[0] * inv, y[1] * inv), __NV_SATFINITE, __NV_E4M3)) |
-                   (static_cast<uint32_t>(__nv_cvt_float2_to_fp8x2(make_float2(y[2] * inv, y[3] * inv), __NV_SATFINITE, __NV_E4M3)) << 16);
-            o8.y = static_cast<uint32_t>(__nv_cvt_float2_to_fp8x2(make_float2(y[4] * inv, y[5] * inv), __NV_SATFINITE, __NV_E4M3)) |
-                   (static_cast<uint32_t>(__nv_cvt_float2_to_fp8x2(make_float2(y[6] * inv, y[7] * inv), __NV_SATFINITE, __NV_E4M3)) << 16);
-            reinterpret_cast<uint2*>(aq + static_cast<long long>(row) * C)[j * 32 + lane] = o8;
-            if ((lane & 3) == 0) {
-                const int kb32 = j * 8 + (lane >> 2);   // 32-column block of this lane quad
-                const int ra = row & 127;
-                const long long chunk = static_cast<long long>(row >> 7) * (C / 128) + (kb32 >> 2);
-                sf[chunk * 512 + ((ra & 31) * 4 + (ra >> 5)) * 4 + (kb32 & 3)] = static_cast<uint8_t>(e);
+                for (int t = 0; t < 8; ++t) y[t] = fmaxf(y[t], 0.f);
+            }
+            if (!QUANT || a) {
+                int4 o;
+                o.x = pack_bf16x2(y[0], y[1]);
+                o.y = pack_bf16x2(y[2], y[3]);
+                o.z = pack_bf16x2(y[4], y[5]);
+                o.w = pack_bf16x2(y[6], y[7]);
+                // asm store with a memory clobber: keeps the compiler from hoisting the parameter loads of all later
+                // chunks above it (which costs 16 registers per chunk and spills)
+                st_v4(reinterpret_cast<int4*>(a + static_cast<long long>(row) * C) + j * 32 + lane, o);
+            }
+            if (QUANT) {
+                float amax = 0.f;
+#pragma unroll
+                for (int t = 0; t < 8; ++t) amax = fmaxf(amax, fabsf(y[t]));
+                amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
+                amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
+                // smallest power-of-two scale with amax / scale <= 448 (same rule as quant_mxfp8_kernel)
+                const uint32_t bits = __float_as_uint(amax * (1.f / 448.f));
+                uint32_t e = ((bits >> 23) & 0xFFu) + ((bits & 0x7FFFFFu) ? 1u : 0u);
+                e = min(max(e, 1u), 253u);
+                const float inv = __uint_as_float((254u - e) << 23);
+                uint2 o8;
+                o8.x = static_cast<uint32_t>(__nv_cvt_float2_to_fp8x2(make_float2(y[0] * inv, y[1] * inv), __NV_SATFINITE, __NV_E4M3)) |
+                       (static_cast<uint32_t>(__nv_cvt_float2_to_fp8x2(make_float2(y[2] * inv, y[3] * inv), __NV_SATFINITE, __NV_E4M3)) << 16);
+                o8.y = static_cast<uint32_t>(__nv_cvt_float2_to_fp8x2(make_float2(y[4] * inv, y[5] * inv), __NV_SATFINITE, __NV_E4M3)) |
+                       (static_cast<uint32_t>(__nv_cvt_float2_to_fp8x2(make_float2(y[6] * inv, y[7] * inv), __NV_SATFINITE, __NV_E4M3)) << 16);
+                asm volatile("st.global.v2.u32 [%0], {%1, %2};" ::"l"(reinterpret_cast<uint2*>(aq + static_cast<long long>(row) * C) + j * 32 + lane),
+                             "r"(o8.x), "r"(o8.y)
+                             : "memory");
+                if ((lane & 3) == 0) {
+                    const int kb32 = j * 8 + (lane >> 2);   // 32-column block of this lane quad
+                    const int ra = row & 127;
+                    const long long chunk = static_cast<long long>(row >> 7) * (C / 128) + (kb32 >> 2);
+                    sf[chunk * 512 + ((ra & 31) * 4 + (ra >> 5)) * 4 + (kb32 & 3)] = static_cast<uint8_t>(e);
+                }
             }
         }
     }
@@ -314,11 +344,15 @@ extern "C" {
 int lah_ln_relu_fwd(const void* h, void* a, float* mean, float* rstd, const float* gamma, const float* beta,
                     const int* tile_group, int rows, int C, int relu, cudaStream_t st) {
     if (rows <= 0) return 0;
-    const int grid = (rows + 7) / 8;
 #define LAH_LN_FWD(CC)                                                                                          \
     if (C == CC) {                                                                                              \
-        ln_relu_fwd_kernel<CC, false><<<grid, 256, 0, st>>>((const bf16*)h, (bf16*)a, mean, rstd, gamma, beta,  \
-                                                            tile_group, rows, relu, nullptr, nullptr);          \
+        constexpr int RR = LnFwdCfg<CC>::R;                                                                     \
+        if (ln_rows_per_warp(RR) == 1)                                                                          \
+            ln_relu_fwd_kernel<CC, false, 1><<<(rows + 7) / 8, 256, 0, st>>>(                                  \
+                (const bf16*)h, (bf16*)a, mean, rstd, gamma, beta, tile_group, rows, relu, nullptr, nullptr);   \
+        else                                                                                                    \
+            ln_relu_fwd_kernel<CC, false, RR><<<(rows + 8 * RR - 1) / (8 * RR), 256, 0, st>>>(                 \
+                (const bf16*)h, (bf16*)a, mean, rstd, gamma, beta, tile_group, rows, relu, nullptr, nullptr);   \
         return -(int)cudaGetLastError();                                                                        \
     }
     LAH_LN_FWD(256) LAH_LN_FWD(512) LAH_LN_FWD(1024) LAH_LN_FWD(2048) LAH_LN_FWD(4096)
@@ -330,11 +364,15 @@ int lah_ln_relu_fwd(const void* h, void* a, float* mean, float* rstd, const floa
 int lah_ln_relu_fwd_q(const void* h, void* a, float* mean, float* rstd, const float* gamma, const float* beta,
                       const int* tile_group, int rows, int C, int relu, void* aq, void* sf, cudaStream_t st) {
     if (rows <= 0) return 0;
-    const int grid = (rows + 7) / 8;
 #define LAH_LN_FWD(CC)                                                                                          \
     if (C == CC) {                                                                                              \
-        ln_relu_fwd_kernel<CC, true><<<grid, 256, 0, st>>>((const bf16*)h, (bf16*)a, mean, rstd, gamma, beta,   \
-                                                           tile_group, rows, relu, (uint8_t*)aq, (uint8_t*)sf); \
+        constexpr int RR = LnFwdCfg<CC>::R;                                                                     \
+        if (ln_rows_per_warp(RR) == 1)                                                                          \
+            ln_relu_fwd_kernel<CC, true, 1><<<(rows + 7) / 8, 256, 0, st>>>(                                  \
+                (const bf16*)h, (bf16*)a, mean, rstd, gamma, beta, tile_group, rows, relu, (uint8_t*)aq, (uint8_t*)sf);   \
+        else                                                                                                    \
+            ln_relu_fwd_kernel<CC, true, RR><<<(rows + 8 * RR - 1) / (8 * RR), 256, 0, st>>>(                 \
+                (const bf16*)h, (bf16*)a, mean, rstd, gamma, beta, tile_group, rows, relu, (uint8_t*)aq, (uint8_t*)sf);   \
         return -(int)cudaGetLastError();                                                                        \
     }
     LAH_LN_FWD(256) LAH_LN_FWD(512) LAH_LN_FWD(1024) LAH_LN_FWD(2048) LAH_LN_FWD(4096)

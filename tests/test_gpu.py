@@ -105,7 +105,7 @@ def test_two_gpu_p2p_dispatch_matches_single_gpu(extra):
     assert "MULTI_GPU_OK" in out.stdout, out.stdout[-3000:]
 
 
-@pytest.mark.parametrize("check", ["check_attention", "check_layer"])
+@pytest.mark.parametrize("check", ["check_attention", "check_layer", "check_ffn_native", "check_chain"])
 def test_attention_kernel_and_native_transformer_expert(check):
     """tcgen05 attention (csrc/attention.cu) and the sm_100a transformer expert vs fp32 PyTorch oracles"""
     from tools import gpu_attention_check as A

@@ -77,12 +77,55 @@ def check_layer():
     print("transformer_perf", results["transformer_perf"], flush=True)
 
 
+def check_ffn_native():
+    """sm_100a forward of the FFN expert (bf16 and MXFP8) vs the fp32 nn.Module; throughput of the fwd-only chain layer"""
+    from lah_b200.models.layers import FeedforwardBlock
+    from lah_b200.models.ffn_native import NativeFFNLayer
+    torch.manual_seed(2)
+    block = FeedforwardBlock(1024).cuda().eval()
+    x = torch.randn(2048, 1024, device="cuda")
+    with torch.no_grad():
+        ref = block(x)
+    xb = x.to(torch.bfloat16)
+    for dtype, tol in (("bf16", 2e-2), ("fp8", 6e-2)):
+        layer = NativeFFNLayer(block, dtype=dtype)
+        out = layer(xb)
+        torch.cuda.synchronize()
+        err = rel(out, ref)
+        big = torch.randn(32768, 1024, device="cuda").to(torch.bfloat16)
+        o2 = torch.empty_like(big)
+        ms = timeit(lambda: layer(big, out=o2))
+        flops = 2.0 * 32768 * 25_165_824
+        results[f"ffn_native_{dtype}"] = dict(ok=err < tol, err=err, ms_32768rows=ms, tflops=flops / ms / 1e9,
+                                              rows_per_s=32768 / ms * 1e3)
+        print(f"ffn_native_{dtype}", results[f"ffn_native_{dtype}"], flush=True)
+    block_bf16 = block.to(torch.bfloat16)
+    with torch.no_grad():
+        ms_t = timeit(lambda: block_bf16(big))
+    results["ffn_torch_bf16"] = dict(ok=True, ms_32768rows=ms_t, rows_per_s=32768 / ms_t * 1e3)
+    print("ffn_torch_bf16", results["ffn_torch_bf16"], flush=True)
+
+
+def check_chain():
+    """in-box throughput experiment, 1 GPU, short chain (plumbing check; the full config runs via the module CLI)"""
+    from lah_b200.experiments.throughput import inbox_chain
+    for bt, dt in (("ffn", "bf16"), ("ffn", "fp8"), ("transformer", "bf16")):
+        args = inbox_chain.make_parser().parse_args(["--block-type", bt, "--layers-per-gpu", "4", "--jobs", "8",
+                                                     "--passes", "2", "--dtype", dt])
+        out = inbox_chain.run(args)
+        results[f"chain_{bt}_{dt}"] = dict(ok=bool(out["ok"]), samples_per_s=out["value"], layer_ms=out["layer_ms"])
+        print(f"chain_{bt}_{dt}", results[f"chain_{bt}_{dt}"], flush=True)
+
+
 if __name__ == "__main__":
-    for fn in (check_attention, check_layer):
+    for fn in (check_attention, check_layer, check_ffn_native, check_chain):
         try:
             fn()
         except Exception as e:  # noqa
             import traceback
             traceback.print_exc()
             results[fn.__name__] = dict(ok=False, error=repr(e))
+    import json
+    os.makedirs("gpurun_out", exist_ok=True)
+    json.dump(results, open("gpurun_out/native_layers_check.json", "w"), indent=1)
     print("ALL_OK" if all(v.get("ok") for v in results.values()) else "SOME_FAILED")
