@@ -261,6 +261,11 @@ def _measure_ours(args, rank, world, local_rank, B, capacity_factor):
                "h2d_bytes_per_step": int(xs_host[0].numel() * 4 + ys_host[0].numel() * 8),
                "d2h_bytes_per_step": 4, "last_loss": losses[-1] if losses else None}
 
+    # per-stage breakdown of ONE extra (untimed) step: CUDA events between the stages, synchronised afterwards
+    trainer.ctx.timer.enabled = True
+    step_device(0)
+    stage_ms = {k: round(v, 3) for k, v in trainer.last_stage_ms.items()}
+    trainer.ctx.timer.enabled = False
     routing = []
     for block in trainer.model.blocks:  # tokens-per-expert histogram of the last step (observability)
         rows = block.ws.step_rows.float()
@@ -283,7 +288,7 @@ def _measure_ours(args, rank, world, local_rank, B, capacity_factor):
                        "gate": cfg.gate_mode + (" (LayerNorm(x) @ normalize(keys); gate params not trained, exactly like the reference's EmulatedDMoE)" if cfg.gate_mode == "emulator" else " (trainable product-key proj, lib.GatingFunction)"),
                        "l2_policy": "working set per step (>35 GB of expert state + >10 GB activations) exceeds the 126 MB L2; no explicit flush"},
             "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "routing_rank0": routing,
-            "exposed_comm_wait_ms_per_step": exposed_ms,
+            "exposed_comm_wait_ms_per_step": exposed_ms, "stage_ms_rank0": stage_ms,
             "baseline_note": "vs_baseline = value / 16.8 samples/s (reference notebook dmoe64x4, BASELINE.md)",
         }
         print(json.dumps(out))

@@ -11,6 +11,7 @@
 // Input : qkv [T = batch*512, 3*D] bf16 (output of the fused in_proj GEMM: [q | k | v] per token, heads contiguous)
 // Output: out [T, D] bf16 (heads concatenated, ready for out_proj)
 #include "sm100.cuh"
+#include <stdlib.h>
 
 namespace lah {
 namespace attn {
@@ -189,6 +190,255 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restric
     }
 }
 
+// ================================================================================================================
+// v2: ping-pong flash attention.  One CTA = one (batch, head, PAIR of 128-query tiles); 10 warps:
+//   warps 0-3 softmax of tile A, warps 4-7 softmax of tile B (thread = query row), warp 8 = MMA issuer, warp 9 = TMA.
+// K / V stream through a 2-stage TMA pipeline in blocks of 128 keys and are shared by both tiles (half the L2 traffic
+// of v1); while the softmax warps of one tile turn S_j into P_j, the tensor core computes S / PV of the other tile, so
+// MUFU (the real bottleneck: 512 exp2 per query row) and tcgen05 overlap.  Online softmax over the 4 key blocks:
+//   m' = max(m, rowmax(S_j)),  alpha = 2^((m - m') * c),  l = l * alpha + sum_k 2^((s_k - m') * c),  O = O * alpha + P_j V_j
+// with O living in TMEM (rescaled in place by the softmax threads: tcgen05.ld -> mul -> tcgen05.st).
+// TMEM: S_A [0,128)  S_B [128,256)  O_A [256,320)  O_B [320,384).
+// ================================================================================================================
+namespace v2 {
+
+constexpr int KB = 128;                       // keys per block
+constexpr int NUM_KB = S_LEN / KB;            // 4
+constexpr int NUM_THREADS2 = 320;
+constexpr int TILE_BYTES = 128 * HEAD_DIM * 2;            // 16 KB: a 128 x 64 bf16 tile (Q tile, K block, V block)
+constexpr int P_BYTES = Q_TILE * KB * 2;                  // 32 KB per query tile
+constexpr int OFF_Q2 = 0;                                 // Q_A, Q_B
+constexpr int OFF_K2 = OFF_Q2 + 2 * TILE_BYTES;           // 2 stages
+constexpr int OFF_V2 = OFF_K2 + 2 * TILE_BYTES;
+constexpr int OFF_P2 = OFF_V2 + 2 * TILE_BYTES;           // P_A, P_B
+constexpr int OFF_BAR2 = OFF_P2 + 2 * P_BYTES;
+constexpr int NUM_BARS = 1 + 8 + 8;
+constexpr int SMEM_TOTAL2 = OFF_BAR2 + NUM_BARS * 8 + 16 + 1024;
+constexpr int COL_S = 0, COL_O = 256;
+
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+        "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+        "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__global__ void __launch_bounds__(NUM_THREADS2, 1)
+attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ out, int d_model, int num_heads,
+                        float scale_log2e) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR2);
+    uint64_t* bar_q = bars;
+    uint64_t* k_full = bars + 1;    // [2]
+    uint64_t* k_empty = bars + 3;   // [2]
+    uint64_t* v_full = bars + 5;    // [2]
+    uint64_t* v_empty = bars + 7;   // [2]
+    uint64_t* s_full = bars + 9;    // [2 tiles]  MMA -> softmax
+    uint64_t* s_free = bars + 11;   // [2 tiles]  softmax (128 threads) -> MMA
+    uint64_t* p_full = bars + 13;   // [2 tiles]  softmax (128 threads) -> MMA
+    uint64_t* pv_done = bars + 15;  // [2 tiles]  MMA -> softmax
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + NUM_BARS);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qpair = blockIdx.x & 1;
+    const int head = (blockIdx.x >> 1) % num_heads;
+    const int batch = (blockIdx.x >> 1) / num_heads;
+    const int seq_row0 = batch * S_LEN;
+
+    if (warp == 9 && lane == 0) {
+        tma_prefetch_desc(&tm_qkv);
+        mbar_init(bar_q, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&k_full[i], 1);
+            mbar_init(&k_empty[i], 1);
+            mbar_init(&v_full[i], 1);
+            mbar_init(&v_empty[i], 1);
+            mbar_init(&s_full[i], 1);
+            mbar_init(&s_free[i], 128);
+            mbar_init(&p_full[i], 128);
+            mbar_init(&pv_done[i], 1);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 8) tmem_alloc(tmem_ptr, 512);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 9) {
+        if (lane == 0) {
+            // ------------------------------------------------------------------ TMA producer
+            mbar_arrive_expect_tx(bar_q, 2 * TILE_BYTES);
+            tma_load_2d(smem + OFF_Q2, &tm_qkv, bar_q, head * HEAD_DIM, seq_row0 + (2 * qpair) * Q_TILE);
+            tma_load_2d(smem + OFF_Q2 + TILE_BYTES, &tm_qkv, bar_q, head * HEAD_DIM, seq_row0 + (2 * qpair + 1) * Q_TILE);
+            for (int j = 0; j < NUM_KB; ++j) {
+                const int st = j & 1;
+                const uint32_t par = ((j >> 1) & 1) ^ 1;
+                mbar_wait(&k_empty[st], par);
+                mbar_arrive_expect_tx(&k_full[st], TILE_BYTES);
+                tma_load_2d(smem + OFF_K2 + st * TILE_BYTES, &tm_qkv, &k_full[st], d_model + head * HEAD_DIM, seq_row0 + j * KB);
+                mbar_wait(&v_empty[st], par);
+                mbar_arrive_expect_tx(&v_full[st], TILE_BYTES);
+                tma_load_2d(smem + OFF_V2 + st * TILE_BYTES, &tm_qkv, &v_full[st], 2 * d_model + head * HEAD_DIM, seq_row0 + j * KB);
+            }
+        }
+    } else if (warp == 8) {
+        if (lane == 0) {
+            // ------------------------------------------------------------------ MMA issuer
+            constexpr uint32_t idesc_s = make_idesc_bf16_f32(Q_TILE, KB, 0u, 0u);
+            constexpr uint32_t idesc_o = make_idesc_bf16_f32(Q_TILE, HEAD_DIM, 0u, 1u);
+            const uint32_t sq = smem_u32(smem + OFF_Q2), sk = smem_u32(smem + OFF_K2), sv = smem_u32(smem + OFF_V2),
+                           sp = smem_u32(smem + OFF_P2);
+            auto issue_s = [&](int t, int j) {
+                const uint32_t a = sq + t * TILE_BYTES, b = sk + (j & 1) * TILE_BYTES;
+#pragma unroll
+                for (int ks = 0; ks < HEAD_DIM / 16; ++ks)
+                    umma_bf16_ss(tmem_base + COL_S + t * KB, make_smem_desc_sw128(a + ks * 32, 0, 1024),
+                                 make_smem_desc_sw128(b + ks * 32, 0, 1024), idesc_s, ks > 0 ? 1u : 0u);
+                umma_commit(&s_full[t]);
+            };
+            mbar_wait(bar_q, 0);
+            mbar_wait(&k_full[0], 0);
+            tcgen05_fence_after();
+            issue_s(0, 0);
+            issue_s(1, 0);
+            umma_commit(&k_empty[0]);
+            for (int j = 0; j < NUM_KB; ++j) {
+                const int st = j & 1;
+                for (int t = 0; t < 2; ++t) {
+                    mbar_wait(&p_full[t], j & 1);
+                    if (t == 0) mbar_wait(&v_full[st], (j >> 1) & 1);
+                    tcgen05_fence_after();
+                    const uint32_t a = sp + t * P_BYTES, b = sv + st * TILE_BYTES;
+#pragma unroll
+                    for (int kb = 0; kb < KB / 64; ++kb) {
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks)
+                            umma_bf16_ss(tmem_base + COL_O + t * HEAD_DIM,
+                                         make_smem_desc_sw128(a + kb * (Q_TILE * 128) + ks * 32, 0, 1024),
+                                         make_smem_desc_sw128(b + (kb * 64 + ks * 16) * 128, 0, 1024), idesc_o,
+                                         (j | kb | ks) ? 1u : 0u);
+                    }
+                    umma_commit(&pv_done[t]);
+                    if (t == 1) umma_commit(&v_empty[st]);
+                    if (j + 1 < NUM_KB) {
+                        if (t == 0) mbar_wait(&k_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
+                        mbar_wait(&s_free[t], j & 1);
+                        tcgen05_fence_after();
+                        issue_s(t, j + 1);
+                        if (t == 1) umma_commit(&k_empty[(j + 1) & 1]);
+                    }
+                }
+            }
+        }
+    } else {
+        // ---------------------------------------------------------------------- softmax + epilogue: thread = query row
+        const int t = warp >> 2;                 // query tile of the pair
+        const int row = (warp & 3) * 32 + lane;  // row inside the tile == TMEM lane
+        const uint32_t lane_base = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+        const uint32_t ts = lane_base + COL_S + t * KB, to = lane_base + COL_O + t * HEAD_DIM;
+        uint8_t* pbase = smem + OFF_P2 + t * P_BYTES;
+        float m = -INFINITY, l = 0.f;
+#pragma unroll 1
+        for (int j = 0; j < NUM_KB; ++j) {
+            mbar_wait(&s_full[t], j & 1);
+            tcgen05_fence_after();
+            float mx = m;
+#pragma unroll 1
+            for (int c = 0; c < KB / 32; ++c) {
+                uint32_t r[32];
+                tmem_ld_32x32(ts + c * 32, r);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+            }
+            const float alpha = exp2f((m - mx) * scale_log2e);   // j == 0: m = -inf -> 0 (O is not touched then)
+            const float mxs = mx * scale_log2e;
+            m = mx;
+            if (j > 0) {   // P buffer free, O_t stable: rescale the running output in place
+                mbar_wait(&pv_done[t], (j - 1) & 1);
+                tcgen05_fence_after();
+#pragma unroll 1
+                for (int c = 0; c < HEAD_DIM / 32; ++c) {
+                    uint32_t r[32];
+                    tmem_ld_32x32(to + c * 32, r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+                    tmem_st_32x32(to + c * 32, r);
+                }
+                tmem_st_wait();
+            }
+            float sum = 0.f;
+#pragma unroll 1
+            for (int c = 0; c < KB / 32; ++c) {
+                uint32_t r[32];
+                tmem_ld_32x32(ts + c * 32, r);
+                tmem_ld_wait();
+                uint32_t packed[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const float p0 = exp2f(__uint_as_float(r[2 * i]) * scale_log2e - mxs);
+                    const float p1 = exp2f(__uint_as_float(r[2 * i + 1]) * scale_log2e - mxs);
+                    const uint32_t pk = pack_bf16x2(p0, p1);
+                    const float2 back = unpack_bf16x2(pk);   // sum what the tensor core will actually see
+                    sum += back.x + back.y;
+                    packed[i] = pk;
+                }
+                // keys [c*32, c*32+32) of the block live in P tile kb = c/2 (64 keys), 16B chunks (c%2)*4 .. +3 of the row
+                uint8_t* tile_row = pbase + (c >> 1) * (Q_TILE * 128) + row * 128;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int chunk = (c & 1) * 4 + q;
+                    int4 v;
+                    v.x = packed[4 * q + 0]; v.y = packed[4 * q + 1]; v.z = packed[4 * q + 2]; v.w = packed[4 * q + 3];
+                    *reinterpret_cast<int4*>(tile_row + ((chunk ^ (row & 7)) << 4)) = v;
+                }
+            }
+            l = l * alpha + sum;
+            tcgen05_fence_before();
+            mbar_arrive(&s_free[t]);        // S_t fully read: the issuer may overwrite it with the next block
+            fence_proxy_async_smem();       // generic-proxy smem writes (P) -> visible to the tensor core
+            mbar_arrive(&p_full[t]);
+        }
+        mbar_wait(&pv_done[t], (NUM_KB - 1) & 1);
+        tcgen05_fence_after();
+        const float inv = 1.f / l;
+        bf16* op = out + static_cast<long long>(seq_row0 + (2 * qpair + t) * Q_TILE + row) * d_model + head * HEAD_DIM;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            uint32_t r[32];
+            tmem_ld_32x32(to + c * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                int4 v;
+                v.x = pack_bf16x2(__uint_as_float(r[8 * i + 0]) * inv, __uint_as_float(r[8 * i + 1]) * inv);
+                v.y = pack_bf16x2(__uint_as_float(r[8 * i + 2]) * inv, __uint_as_float(r[8 * i + 3]) * inv);
+                v.z = pack_bf16x2(__uint_as_float(r[8 * i + 4]) * inv, __uint_as_float(r[8 * i + 5]) * inv);
+                v.w = pack_bf16x2(__uint_as_float(r[8 * i + 6]) * inv, __uint_as_float(r[8 * i + 7]) * inv);
+                *reinterpret_cast<int4*>(op + c * 32 + 8 * i) = v;
+            }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 8) {
+        tcgen05_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+}  // namespace v2
+
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -222,15 +472,24 @@ int lah_attention_fwd(const void* qkv, void* out, int batch, int num_heads, int 
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return -1000 - (int)r;
     static bool configured = false;
+    static int use_v1 = 0;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
         if (e != cudaSuccess) return -(int)e;
+        e = cudaFuncSetAttribute(v2::attention_fwd_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::SMEM_TOTAL2);
+        if (e != cudaSuccess) return -(int)e;
+        const char* env = getenv("LAH_ATTN_V1");   // A/B switch: the one-tile-per-CTA kernel
+        use_v1 = env && atoi(env) == 1;
         configured = true;
     }
-    const int grid = batch * num_heads * (S_LEN / Q_TILE);
-    if (grid <= 0) return 0;
+    if (batch <= 0) return 0;
     const float scale_log2e = 1.4426950408889634f / sqrtf((float)HEAD_DIM);
-    attention_fwd_kernel<<<grid, NUM_THREADS, SMEM_TOTAL, st>>>(tm, (bf16*)out, d_model, num_heads, scale_log2e);
+    if (use_v1)
+        attention_fwd_kernel<<<batch * num_heads * (S_LEN / Q_TILE), NUM_THREADS, SMEM_TOTAL, st>>>(tm, (bf16*)out, d_model,
+                                                                                              num_heads, scale_log2e);
+    else
+        v2::attention_fwd_v2_kernel<<<batch * num_heads * 2, v2::NUM_THREADS2, v2::SMEM_TOTAL2, st>>>(
+            tm, (bf16*)out, d_model, num_heads, scale_log2e);
     return -(int)cudaGetLastError();
 }
 

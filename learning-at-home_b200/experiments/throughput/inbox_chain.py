@@ -111,7 +111,7 @@ def run(args):
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms)
-    ok = int(status.item()) == 0 and bool(torch.isfinite(bufs[0].float()).all())
+    ok = int(status[0].item()) == 0 and bool(torch.isfinite(bufs[0].float()).all())
     samples = args.jobs * batch * args.passes
     out = dict(metric="throughput experiment samples/s (forward, device-timed, max over ranks)", value=samples / ms * 1e3,
                unit="samples/s (sequences of 512 tokens)" if transformer else "samples/s (rows)", n_gpus=world,

@@ -140,6 +140,8 @@ class EngineContext:
         self.alive = torch.ones(self.E, dtype=torch.uint8, device=self.device)
         self.epoch = 0
         self.token_counter = 0
+        from .profiler import StageTimer
+        self.timer = StageTimer(enabled=False)   # DMoETrainer(profile_stages=True) switches it on
         # transient backward buffers shared by all layers
         self.gyd, self.gyd_off = self.heap.alloc((self.max_rows, H), torch.bfloat16)
         self.dxd, self.dxd_off = self.heap.alloc((self.max_rows, H), torch.bfloat16)
@@ -408,6 +410,7 @@ class FusedDMoE(nn.Module):
                     seed=cfg.seed * 7919 + self.layer_index, token_offset=c.token_counter, idx=idx, w=w, pos=pos,
                     counts=c.counts)
         c.token_counter += B
+        c.timer.mark("gate_topk")
         K.layout_exchange(c.cnt_all_off, c.flags_off, K.SLOT_COUNTS, epoch, c.E, c.E_loc, c.max_rows, align=c.align,
                           counts=c.counts,
                           dst_row=ws.dst_row, group_off=ws.group_off, group_rows=ws.group_rows,
@@ -420,6 +423,7 @@ class FusedDMoE(nn.Module):
         K.scatter_rows(x, None, idx, pos, ws.dst_row, pair_row, ws.xd_off, c.flags_off, K.SLOT_DISPATCH, epoch, k,
                        c.E_loc, c.max_rows, ws.group_off, ws.group_rows, c.done_counter, c.status, align=c.align,
                        route_owner=ws.route_owner, num_groups=c.G_tot)
+        c.timer.mark("dispatch(layout+pull+scatter)")
         # ---- expert FFN on the rows this rank received (grouped by expert).  Receive-side fusion: the first GEMM's TMA
         # producer polls the peers' dispatch flags itself (no separate wait kernel)
         tg = ws.tile_group
@@ -434,9 +438,11 @@ class FusedDMoE(nn.Module):
             K.ln_relu_fwd(ws.h2, sh.views["g2"], sh.views["be2"], tg, out=ws.a2, mean=ws.mean2, rstd=ws.rstd2)
             gemm.grouped_linear(ws.a2, sh.bf16["w3"], tile_group=tg, bias=sh.views["b3"], residual=ws.xd, out=ws.yo,
                                 two_cta=c.two_cta)
+        c.timer.mark("expert_ffn_fwd")
         y = torch.empty(B, cfg.hidden, dtype=torch.bfloat16, device=x.device)
         K.combine_rows(ws.yo_off, idx, pair_row, w, y, k, c.E_loc, flags_off=c.flags_off, slot=K.SLOT_OUTPUT, epoch=epoch,
                        signal=c.world > 1, wait=c.world > 1, status=c.status, route_owner=ws.route_owner)
+        c.timer.mark("combine")
         return y
 
     def _expert_ffn_fp8(self, wait, epoch):
@@ -471,6 +477,7 @@ class FusedDMoE(nn.Module):
             K.zero_slots(sh.g, sh.seg_sizes, c.G_tot, c.E_loc, c.S, SMALL_SEG_MASK)
         if c.world > 1:  # the first consumers of the pushed gradients are the colsum / wgrad kernels
             K.signal_wait(c.flags_off, K.SLOT_GRAD, epoch, c.status, signal=False, wait=True)
+        c.timer.mark("bwd_gate+dispatch_grad")
         tg, go, G = ws.tile_group, ws.group_off, c.G_tot
         gr = sh.grads
         K.grouped_colsum(c.gyd, tg, out=gr["b3"])
@@ -485,13 +492,16 @@ class FusedDMoE(nn.Module):
         gemm.grouped_wgrad(c.dh, ws.xd, go, G, out=gr["w1"], two_cta=c.two_cta)
         gemm.grouped_linear(c.dh, sh.bf16["w1"], tile_group=tg, w_is_kn=True, residual=c.gyd, out=c.dxd,
                             two_cta=c.two_cta)
+        c.timer.mark("expert_ffn_bwd(wgrad+dgrad+ln)")
         # ---- expert-side optimizer step (reference: ExpertBackend.apply_gradients right after backward)
         if c.S:  # the owners read every rank's partial gradients of the shadowed experts: all ranks must be done
             K.signal_wait(c.flags_off, K.SLOT_SHADOW, epoch, c.status, signal=True, wait=True)
         self.apply_expert_gradients()
+        c.timer.mark("expert_adam")
         dx = torch.empty(B, cfg.hidden, dtype=torch.bfloat16, device=gy.device)
         K.combine_rows(c.dxd_off, idx, pair_row, None, dx, k, c.E_loc, flags_off=c.flags_off, slot=K.SLOT_DINPUT,
                        epoch=epoch, signal=c.world > 1, wait=c.world > 1, status=c.status, route_owner=ws.route_owner)
+        c.timer.mark("bwd_combine")
         return dx, dlogits
 
     def apply_expert_gradients(self):

@@ -23,14 +23,24 @@ from .engine import DMoEConfig, EngineContext, DMoEClassifier
 
 
 class DMoETrainer:
-    def __init__(self, cfg: DMoEConfig, group=None, device: Optional[torch.device] = None):
+    def __init__(self, cfg: DMoEConfig, group=None, device: Optional[torch.device] = None, profile_stages: bool = False,
+                 metrics_path: Optional[str] = None):
+        """
+        :param profile_stages: time every stage of a step with CUDA events (+ NVTX ranges); see ``last_stage_ms``
+        :param metrics_path: append one JSON record per ``log_step()`` call to this file (structured step metrics)
+        """
+        from .profiler import MetricsLog
         self.cfg = cfg
+        self.metrics = MetricsLog(metrics_path)
+        self.last_stage_ms = {}
         self.cuda = torch.cuda.is_available() and (device is None or torch.device(device).type == "cuda")
         if self.cuda:
             native.have_cuda_kernels()  # loads liblah_cuda.so or raises: no silent fallback on a GPU box
             self.ctx = EngineContext(cfg, group=group, device=device)
             self.device = self.ctx.device
             self.world, self.rank = self.ctx.world, self.ctx.rank
+            self.ctx.timer.enabled = profile_stages
+            self.ctx.timer.nvtx = profile_stages
         else:
             self.ctx, self.device, self.world, self.rank = None, torch.device("cpu"), 1, 0
         torch.manual_seed(cfg.seed)  # identical trainer parameters on every rank
@@ -101,14 +111,48 @@ class DMoETrainer:
     def train_step_device(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
         """one optimisation step on device tensors; returns the (device) loss tensor, no host synchronisation"""
         self.model.train()
+        timer = self.ctx.timer if self.cuda else None
+        if timer is not None:
+            timer.start()
         logits = self.model(x)
         loss = F.cross_entropy(logits.float(), y)
+        if timer is not None:
+            timer.mark("head+loss")
         loss.backward()  # expert updates happen inside (server-side semantics), trainer grads land in flat_g
         if not self.cuda:
             for block in self.model.blocks:
                 block.apply_expert_gradients_ref()
+        if timer is not None:
+            timer.mark("trainer_bwd(stem+gates)")
         self._trainer_optimizer_step()
+        if timer is not None:
+            timer.mark("trainer_adam")
+            if timer.enabled:
+                self.last_stage_ms = timer.report()
         return loss.detach()
+
+    def log_step(self, loss=None, samples=None, step_ms=None, **extra):
+        """structured step record: routing statistics of every DMoE layer, exposed communication wait,
+        per-stage ms (when profile_stages), throughput; written to ``metrics_path`` and returned"""
+        rec = dict(step=self.step_count, rank=self.rank, world=self.world)
+        if loss is not None:
+            rec["loss"] = float(loss)
+        if samples is not None and step_ms:
+            rec["samples_per_s"] = samples / step_ms * 1e3
+            rec["step_ms"] = step_ms
+        if self.cuda:
+            rec["exposed_comm_wait_ms"] = self.ctx.exposed_wait_ms(reset=True)
+            layers = []
+            for block in self.model.blocks:
+                rows = block.ws.step_rows.float()
+                layers.append(dict(active_experts=int((rows > 0).sum()), max_rows=int(rows.max()),
+                                   mean_rows=float(rows.mean()), padded_rows=int(block.ws.total_rows.item()),
+                                   shadowed_experts=int((block.ws.shadow_info.view(-1, 4)[:, 0] >= 0).sum())))
+            rec["layers"] = layers
+            if self.last_stage_ms:
+                rec["stage_ms"] = dict(self.last_stage_ms)
+        rec.update(extra)
+        return self.metrics.write(**rec)
 
     def train_step(self, x_host: torch.Tensor, y_host: torch.Tensor) -> float:
         """END-TO-END step: host (pinned) inputs -> H2D -> fwd/bwd/optimizers -> D2H loss -> python float"""

@@ -211,3 +211,24 @@ def test_mxfp8_reference_quantiser_roundtrip():
     assert bool((back[3] == 0).all())
     assert fp8.sf_bytes(2048, 3, 512, fp8.WEIGHT_TILE) == 11 * 4 * 2 * 3 * 512
     assert fp8.sf_bytes(384, 1, 512, fp8.ACT_TILE) == 3 * 4 * 512
+
+
+def test_metrics_log_and_stage_timer(tmp_path):
+    """structured JSONL step metrics and the (disabled-by-default) stage timer"""
+    import json
+    from lah_b200.parallel.profiler import MetricsLog, StageTimer
+    from lah_b200.parallel.engine import DMoEConfig
+    from lah_b200.parallel.trainer import DMoETrainer
+    t = StageTimer(enabled=False)
+    t.start(), t.mark("a")
+    assert t.report() == {}
+    path = tmp_path / "m" / "steps.jsonl"
+    cfg = DMoEConfig(hidden=32, grid_size=(2, 2), k=2, num_layers=1, in_features=8, tokens_per_rank=16)
+    trainer = DMoETrainer(cfg, device="cpu", metrics_path=str(path))
+    x, y = torch.randn(16, 8), torch.randint(0, 10, (16,))
+    loss = trainer.train_step(x, y)
+    rec = trainer.log_step(loss=loss, samples=16, step_ms=2.0, note="cpu")
+    assert rec["samples_per_s"] == 8000.0 and rec["step"] == 1
+    trainer.metrics.close()
+    lines = [json.loads(l) for l in open(path)]
+    assert len(lines) == 1 and lines[0]["note"] == "cpu" and abs(lines[0]["loss"] - loss) < 1e-6
