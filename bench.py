@@ -214,7 +214,9 @@ def _measure_ours(args, rank, world, local_rank, B, capacity_factor):
     losses = []
 
     def step_e2e(i):
-        losses.append(trainer.train_step(xs_host[i % n_batches], ys_host[i % n_batches]))
+        nxt = (i + 1) % n_batches   # the next step's inputs cross PCIe on a copy stream while this step computes
+        losses.append(trainer.train_step(xs_host[i % n_batches], ys_host[i % n_batches],
+                                         prefetch=(xs_host[nxt], ys_host[nxt])))
 
     def check_all_ranks():
         code = int(trainer.ctx.status.item())

@@ -314,6 +314,13 @@ attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __rest
             for (int j = 0; j < NUM_KB; ++j) {
                 const int st = j & 1;
                 for (int t = 0; t < 2; ++t) {
+                    if (j + 1 < NUM_KB) {   // S of the NEXT block first: the softmax warps hold S_t(j) in registers already
+                        if (t == 0) mbar_wait(&k_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
+                        mbar_wait(&s_free[t], j & 1);
+                        tcgen05_fence_after();
+                        issue_s(t, j + 1);
+                        if (t == 1) umma_commit(&k_empty[(j + 1) & 1]);
+                    }
                     mbar_wait(&p_full[t], j & 1);
                     if (t == 0) mbar_wait(&v_full[st], (j >> 1) & 1);
                     tcgen05_fence_after();
@@ -329,13 +336,6 @@ attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __rest
                     }
                     umma_commit(&pv_done[t]);
                     if (t == 1) umma_commit(&v_empty[st]);
-                    if (j + 1 < NUM_KB) {
-                        if (t == 0) mbar_wait(&k_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
-                        mbar_wait(&s_free[t], j & 1);
-                        tcgen05_fence_after();
-                        issue_s(t, j + 1);
-                        if (t == 1) umma_commit(&k_empty[(j + 1) & 1]);
-                    }
                 }
             }
         }
@@ -346,48 +346,56 @@ attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __rest
         const uint32_t lane_base = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
         const uint32_t ts = lane_base + COL_S + t * KB, to = lane_base + COL_O + t * HEAD_DIM;
         uint8_t* pbase = smem + OFF_P2 + t * P_BYTES;
+        // m = the reference maximum the probabilities are currently expressed against (raw score units).  LAZY rescale:
+        // m only moves when the row maximum grew by more than 8 / scale_log2e, i.e. probabilities stay below 2^8 — exact
+        // after the final division by l, and the TMEM round trip of O (ld -> mul -> st) is skipped for most blocks.
         float m = -INFINITY, l = 0.f;
+        const float lazy_margin = 8.f / scale_log2e;
 #pragma unroll 1
         for (int j = 0; j < NUM_KB; ++j) {
             mbar_wait(&s_full[t], j & 1);
             tcgen05_fence_after();
-            float mx = m;
-#pragma unroll 1
-            for (int c = 0; c < KB / 32; ++c) {
-                uint32_t r[32];
-                tmem_ld_32x32(ts + c * 32, r);
-                tmem_ld_wait();
+            uint32_t r[KB / 32][32];   // the whole 128-score row of this block: one pass over TMEM
 #pragma unroll
-                for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+            for (int c = 0; c < KB / 32; ++c) tmem_ld_32x32(ts + c * 32, r[c]);
+            tmem_ld_wait();
+            tcgen05_fence_before();
+            mbar_arrive(&s_free[t]);   // S_t is in registers: the issuer may already compute the next block's S_t
+            float mx = -INFINITY;
+#pragma unroll
+            for (int c = 0; c < KB / 32; ++c)
+#pragma unroll
+                for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[c][i]));
+            float alpha = 1.f;
+            if (mx > m + lazy_margin || j == 0) {
+                alpha = exp2f((m - mx) * scale_log2e);   // j == 0: m = -inf -> 0 (O is not read then)
+                m = mx;
             }
-            const float alpha = exp2f((m - mx) * scale_log2e);   // j == 0: m = -inf -> 0 (O is not touched then)
-            const float mxs = mx * scale_log2e;
-            m = mx;
-            if (j > 0) {   // P buffer free, O_t stable: rescale the running output in place
+            const float ms = m * scale_log2e;
+            if (j > 0) {   // P buffer free and O_t stable once PV_t(j-1) completed
                 mbar_wait(&pv_done[t], (j - 1) & 1);
                 tcgen05_fence_after();
+                if (__any_sync(0xffffffffu, alpha != 1.f)) {   // rescale the running output in place (warp-collective)
 #pragma unroll 1
-                for (int c = 0; c < HEAD_DIM / 32; ++c) {
-                    uint32_t r[32];
-                    tmem_ld_32x32(to + c * 32, r);
-                    tmem_ld_wait();
+                    for (int c = 0; c < HEAD_DIM / 32; ++c) {
+                        uint32_t o[32];
+                        tmem_ld_32x32(to + c * 32, o);
+                        tmem_ld_wait();
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
-                    tmem_st_32x32(to + c * 32, r);
+                        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                        tmem_st_32x32(to + c * 32, o);
+                    }
+                    tmem_st_wait();
                 }
-                tmem_st_wait();
             }
             float sum = 0.f;
-#pragma unroll 1
+#pragma unroll
             for (int c = 0; c < KB / 32; ++c) {
-                uint32_t r[32];
-                tmem_ld_32x32(ts + c * 32, r);
-                tmem_ld_wait();
                 uint32_t packed[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                    const float p0 = exp2f(__uint_as_float(r[2 * i]) * scale_log2e - mxs);
-                    const float p1 = exp2f(__uint_as_float(r[2 * i + 1]) * scale_log2e - mxs);
+                    const float p0 = exp2f(__uint_as_float(r[c][2 * i]) * scale_log2e - ms);
+                    const float p1 = exp2f(__uint_as_float(r[c][2 * i + 1]) * scale_log2e - ms);
                     const uint32_t pk = pack_bf16x2(p0, p1);
                     const float2 back = unpack_bf16x2(pk);   // sum what the tensor core will actually see
                     sum += back.x + back.y;
@@ -405,7 +413,6 @@ attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __rest
             }
             l = l * alpha + sum;
             tcgen05_fence_before();
-            mbar_arrive(&s_free[t]);        // S_t fully read: the issuer may overwrite it with the next block
             fence_proxy_async_smem();       // generic-proxy smem writes (P) -> visible to the tensor core
             mbar_arrive(&p_full[t]);
         }

@@ -26,7 +26,7 @@ constexpr int CTA_N = 96;     // B rows loaded per CTA
 constexpr int BLOCK_K = 128;  // elements == bytes
 constexpr int UMMA_K = 32;
 constexpr int STAGES = 6;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 320;   // TMA warp, MMA warp, up to 8 epilogue warps
 
 constexpr int A_BYTES = CTA_M * BLOCK_K;        // 16 KB
 constexpr int B_BYTES = CTA_N * BLOCK_K;        // 12 KB
@@ -36,10 +36,9 @@ constexpr int STAGE_TX = A_BYTES + B_BYTES + SFA_BYTES + SFB_BYTES;
 constexpr int STAGE_BYTES = 30 * 1024;          // padded to a multiple of 1024 (swizzle atom alignment)
 constexpr int SFA_OFF = A_BYTES + B_BYTES;
 constexpr int SFB_OFF = SFA_OFF + SFA_BYTES;
-constexpr int EPI_ROW_BYTES = 144;
-constexpr int EPI_WARP_BYTES = 32 * EPI_ROW_BYTES;
 constexpr int EPI_OFFSET = STAGES * STAGE_BYTES;
-constexpr int BAR_OFFSET = EPI_OFFSET + 4 * EPI_WARP_BYTES;
+constexpr int EPI_BYTES = 8 * 32 * 80;          // max(8 warps x 32 rows x 80 B (bf16), 4 warps x 32 rows x 144 B (fp32))
+constexpr int BAR_OFFSET = EPI_OFFSET + EPI_BYTES;
 constexpr int SMEM_TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 1024;
 constexpr int TMEM_SFA_COL = 2 * TILE_N;        // 384
 constexpr int TMEM_SFB_COL = TMEM_SFA_COL + 4;  // 388 .. 395
@@ -103,6 +102,12 @@ gemm_fp8_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const _
     uint64_t* tmem_empty = tmem_full + 2;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
+    // epilogue geometry: 32-column chunks; a chunk row is 64 B (bf16) or 128 B (fp32) + 16 B pad in the staging slab
+    constexpr int EPI_WARPS = OUT_F32 ? 4 : 8;
+    constexpr int EPI_ROW_BYTES = OUT_F32 ? 144 : 80;
+    constexpr int EPI_WARP_BYTES = 32 * EPI_ROW_BYTES;
+    static_assert(EPI_WARPS * EPI_WARP_BYTES <= EPI_BYTES, "epilogue staging");
+
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const uint32_t cta_rank = cluster_ctarank();
@@ -119,7 +124,7 @@ gemm_fp8_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const _
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tmem_full[i], 1);
-            mbar_init(&tmem_empty[i], 8);
+            mbar_init(&tmem_empty[i], 2 * EPI_WARPS);   // every epilogue warp of both CTAs
         }
         fence_mbar_init();
     }
@@ -216,9 +221,14 @@ gemm_fp8_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const _
             }
             ++iter;
         }
-    } else if (warp >= 2) {
+    } else if (warp >= 2 && warp < 2 + EPI_WARPS) {
         // =============================================================== epilogue (both CTAs; own 128 rows)
+        // bf16 output: EIGHT warps — two per TMEM lane quadrant, interleaved over the 32-column chunks.  With four warps
+        // one warp per SM sub-partition walked a ~100-instruction dependent chain per chunk (tcgen05.ld -> bias ->
+        // pack -> smem transpose -> stores) and the drain of a tile took longer than its MMAs (ncu: tensor pipe 46 %).
         const int lane_group = warp & 3;
+        const int chunk_first = (warp - 2) >> 2;             // 0 or 1 (always 0 with four warps)
+        constexpr int CHUNK_STEP = EPI_WARPS / 4;
         int iter = 0;
         for (int tile = pair_id; tile < total_tiles; tile += num_pairs) {
             int m_tile, n_tile, g;
@@ -232,81 +242,75 @@ gemm_fp8_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const _
             const int row = row_base + lane;
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_group * 32) << 16) + as * TILE_N;
             uint8_t* slab = smem + EPI_OFFSET + (warp - 2) * EPI_WARP_BYTES;
-            constexpr int COLS_PER_ITER = OUT_F32 ? 32 : 64;
 #pragma unroll 1
-            for (int c0 = 0; c0 < TILE_N; c0 += COLS_PER_ITER) {
-                if (n_col + c0 >= p.N) break;  // tail tile (N % 192 != 0): columns past N are never stored
+            for (int c0 = chunk_first * 32; c0 < TILE_N; c0 += CHUNK_STEP * 32) {
+                const int col = n_col + c0;
+                if (col >= p.N) break;  // tail tile (N % 192 != 0): columns past N are never stored
+                uint32_t r[32];
+                tmem_ld_32x32(taddr + c0, r);
+                tmem_ld_wait();
+                float v[32];
 #pragma unroll
-                for (int hf = 0; hf < COLS_PER_ITER / 32; ++hf) {
-                    uint32_t r[32];
-                    tmem_ld_32x32(taddr + c0 + hf * 32, r);
-                    tmem_ld_wait();
-                    const int col = n_col + c0 + hf * 32;
-                    float v[32];
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                if (p.bias) {
+                    const float4* bp = reinterpret_cast<const float4*>(p.bias + static_cast<long long>(g) * p.N + col);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                    if (col < p.N) {
-                        if (p.bias) {
-                            const float4* bp = reinterpret_cast<const float4*>(p.bias + static_cast<long long>(g) * p.N + col);
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                const float4 b = __ldg(bp + j);
-                                v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
-                            }
-                        }
-                        if (p.act == 1) {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-                        } else if (p.act == 2) {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) v[j] = 0.5f * v[j] * (1.f + erff(v[j] * 0.70710678118654752f));
-                        }
-                        if (p.residual && row < p.M) {
-                            const int4* rp = reinterpret_cast<const int4*>(p.residual + static_cast<long long>(row) * p.ldr + col);
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const int4 q = __ldg(rp + j);
-                                const uint32_t w[4] = {(uint32_t)q.x, (uint32_t)q.y, (uint32_t)q.z, (uint32_t)q.w};
-#pragma unroll
-                                for (int t = 0; t < 4; ++t) {
-                                    const float2 f = unpack_bf16x2(w[t]);
-                                    v[8 * j + 2 * t] += f.x;
-                                    v[8 * j + 2 * t + 1] += f.y;
-                                }
-                            }
-                        }
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 b = __ldg(bp + j);
+                        v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
                     }
-                    uint8_t* my = slab + lane * EPI_ROW_BYTES;
-                    if (OUT_F32) {
+                }
+                if (p.act == 1) {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            *reinterpret_cast<float4*>(my + 16 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                    } else {
+                    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+                } else if (p.act == 2) {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            int4 q;
-                            q.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
-                            q.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-                            q.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
-                            q.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
-                            *reinterpret_cast<int4*>(my + hf * 64 + 16 * j) = q;
+                    for (int j = 0; j < 32; ++j) v[j] = 0.5f * v[j] * (1.f + erff(v[j] * 0.70710678118654752f));
+                }
+                if (p.residual && row < p.M) {
+                    const int4* rp = reinterpret_cast<const int4*>(p.residual + static_cast<long long>(row) * p.ldr + col);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int4 q = __ldg(rp + j);
+                        const uint32_t w[4] = {(uint32_t)q.x, (uint32_t)q.y, (uint32_t)q.z, (uint32_t)q.w};
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) {
+                            const float2 f = unpack_bf16x2(w[t]);
+                            v[8 * j + 2 * t] += f.x;
+                            v[8 * j + 2 * t + 1] += f.y;
                         }
                     }
                 }
-                __syncwarp();
-                const int chunk = lane & 7;
-                const int elem = OUT_F32 ? 4 : 2;
-                const int col_lo = n_col + c0 + chunk * (16 / elem);   // first column of this lane's 16 B
-                uint8_t* cbase = reinterpret_cast<uint8_t*>(p.C) + static_cast<long long>(col_lo) * elem;
-                const long long row_bytes = p.ldc * elem;
-                if (col_lo < p.N) {
+                // transpose through a padded smem slab so that the global stores are row-contiguous
+                uint8_t* my = slab + lane * EPI_ROW_BYTES;
+                if (OUT_F32) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int rl = i * 4 + (lane >> 3);
-                        const int grow = row_base + rl;
-                        const int4 q = *reinterpret_cast<const int4*>(slab + rl * EPI_ROW_BYTES + chunk * 16);
-                        if (grow < p.M) *reinterpret_cast<int4*>(cbase + static_cast<long long>(grow) * row_bytes) = q;
+                    for (int j = 0; j < 8; ++j)
+                        *reinterpret_cast<float4*>(my + 16 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        int4 q;
+                        q.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+                        q.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+                        q.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+                        q.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+                        *reinterpret_cast<int4*>(my + 16 * j) = q;
                     }
+                }
+                __syncwarp();
+                constexpr int ELEM = OUT_F32 ? 4 : 2;
+                constexpr int LANES_PER_ROW = 32 * ELEM / 16;        // 16 B pieces of a 32-column row segment: 8 / 4
+                constexpr int ROWS_PER_INSTR = 32 / LANES_PER_ROW;   // 4 / 8
+                const int piece = lane % LANES_PER_ROW;
+                uint8_t* cbase = reinterpret_cast<uint8_t*>(p.C) + (static_cast<long long>(col) * ELEM + piece * 16);
+                const long long row_bytes = p.ldc * ELEM;
+#pragma unroll
+                for (int i = 0; i < 32 / ROWS_PER_INSTR; ++i) {
+                    const int rl = i * ROWS_PER_INSTR + lane / LANES_PER_ROW;
+                    const int grow = row_base + rl;
+                    const int4 q = *reinterpret_cast<const int4*>(slab + rl * EPI_ROW_BYTES + piece * 16);
+                    if (grow < p.M) *reinterpret_cast<int4*>(cbase + static_cast<long long>(grow) * row_bytes) = q;
                 }
                 __syncwarp();
             }

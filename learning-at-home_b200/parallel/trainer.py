@@ -49,8 +49,14 @@ class DMoETrainer:
         self.step_count = 0
         B = cfg.tokens_per_rank
         if self.cuda:
-            self._x_dev = torch.empty(B, cfg.in_features, device=self.device)
-            self._y_dev = torch.empty(B, dtype=torch.int64, device=self.device)
+            # double-buffered staging: the NEXT step's inputs can cross PCIe on a copy stream while this step computes
+            self._x_dev = [torch.empty(B, cfg.in_features, device=self.device) for _ in range(2)]
+            self._y_dev = [torch.empty(B, dtype=torch.int64, device=self.device) for _ in range(2)]
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._copy_done = [torch.cuda.Event(), torch.cuda.Event()]
+            self._compute_done = [torch.cuda.Event(), torch.cuda.Event()]
+            self._staged = [None, None]   # (id(x_host), id(y_host), rows) currently resident in each staging buffer
+            self._slot = 0
             self._loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
 
     # ------------------------------------------------------------------ trainer-side flat parameters
@@ -154,17 +160,37 @@ class DMoETrainer:
         rec.update(extra)
         return self.metrics.write(**rec)
 
-    def train_step(self, x_host: torch.Tensor, y_host: torch.Tensor) -> float:
-        """END-TO-END step: host (pinned) inputs -> H2D -> fwd/bwd/optimizers -> D2H loss -> python float"""
+    def _stage(self, slot, x_host, y_host):
+        """enqueue the H2D copies of one batch into staging buffer `slot` on the copy stream"""
+        B = x_host.shape[0]
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(self._compute_done[slot])   # the previous user of this buffer has finished
+            self._x_dev[slot][:B].copy_(x_host, non_blocking=True)
+            self._y_dev[slot][:B].copy_(y_host, non_blocking=True)
+            self._copy_done[slot].record(self._copy_stream)
+        self._staged[slot] = (id(x_host), id(y_host), B)
+
+    def train_step(self, x_host: torch.Tensor, y_host: torch.Tensor, prefetch=None) -> float:
+        """END-TO-END step: host (pinned) inputs -> H2D -> fwd/bwd/optimizers -> D2H loss -> python float.
+
+        :param prefetch: optional ``(x_next, y_next)`` pinned host tensors of the NEXT call: their H2D copy is started
+            now on a copy stream and overlaps this step's compute (the next call then finds its inputs on the device)."""
         if not self.cuda:
             return float(self.train_step_device(x_host, y_host))
         B = x_host.shape[0]
-        x, y = self._x_dev[:B], self._y_dev[:B]
-        x.copy_(x_host, non_blocking=True)
-        y.copy_(y_host, non_blocking=True)
-        loss = self.train_step_device(x, y)
+        slot = self._slot
+        if self._staged[slot] != (id(x_host), id(y_host), B):
+            self._stage(slot, x_host, y_host)
+        stream = torch.cuda.current_stream(self.device)
+        stream.wait_event(self._copy_done[slot])
+        if prefetch is not None:
+            self._stage(slot ^ 1, *prefetch)
+        loss = self.train_step_device(self._x_dev[slot][:B], self._y_dev[slot][:B])
+        self._compute_done[slot].record(stream)
+        self._staged[slot] = None
+        self._slot = slot ^ 1
         self._loss_host.copy_(loss.reshape(1), non_blocking=True)
-        torch.cuda.current_stream(self.device).synchronize()
+        stream.synchronize()
         return float(self._loss_host[0])
 
     @torch.no_grad()
