@@ -229,7 +229,7 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-__global__ void __launch_bounds__(NUM_THREADS2, 1)
+__global__ void __maxnreg__(200)
 attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ out, int d_model, int num_heads,
                         float scale_log2e) {
     extern __shared__ uint8_t smem_raw[];
@@ -361,11 +361,16 @@ attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __rest
             tmem_ld_wait();
             tcgen05_fence_before();
             mbar_arrive(&s_free[t]);   // S_t is in registers: the issuer may already compute the next block's S_t
-            float mx = -INFINITY;
+            // 8 independent max chains (a single 128-deep fmaxf chain is 128 x the ALU latency on the critical path)
+            float mxs8[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) mxs8[i] = -INFINITY;
 #pragma unroll
             for (int c = 0; c < KB / 32; ++c)
 #pragma unroll
-                for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[c][i]));
+                for (int i = 0; i < 32; ++i) mxs8[i & 7] = fmaxf(mxs8[i & 7], __uint_as_float(r[c][i]));
+            const float mx = fmaxf(fmaxf(fmaxf(mxs8[0], mxs8[1]), fmaxf(mxs8[2], mxs8[3])),
+                                   fmaxf(fmaxf(mxs8[4], mxs8[5]), fmaxf(mxs8[6], mxs8[7])));
             float alpha = 1.f;
             if (mx > m + lazy_margin || j == 0) {
                 alpha = exp2f((m - mx) * scale_log2e);   // j == 0: m = -inf -> 0 (O is not read then)
@@ -388,7 +393,7 @@ attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __rest
                     tmem_st_wait();
                 }
             }
-            float sum = 0.f;
+            float sum4[4] = {0.f, 0.f, 0.f, 0.f};   // independent partial sums: short dependency chains
 #pragma unroll
             for (int c = 0; c < KB / 32; ++c) {
                 uint32_t packed[16];
@@ -398,7 +403,7 @@ attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __rest
                     const float p1 = exp2f(__uint_as_float(r[c][2 * i + 1]) * scale_log2e - ms);
                     const uint32_t pk = pack_bf16x2(p0, p1);
                     const float2 back = unpack_bf16x2(pk);   // sum what the tensor core will actually see
-                    sum += back.x + back.y;
+                    sum4[i & 3] += back.x + back.y;
                     packed[i] = pk;
                 }
                 // keys [c*32, c*32+32) of the block live in P tile kb = c/2 (64 keys), 16B chunks (c%2)*4 .. +3 of the row
@@ -411,7 +416,7 @@ attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __rest
                     *reinterpret_cast<int4*>(tile_row + ((chunk ^ (row & 7)) << 4)) = v;
                 }
             }
-            l = l * alpha + sum;
+            l = l * alpha + ((sum4[0] + sum4[1]) + (sum4[2] + sum4[3]));
             tcgen05_fence_before();
             fence_proxy_async_smem();       // generic-proxy smem writes (P) -> visible to the tensor core
             mbar_arrive(&p_full[t]);
