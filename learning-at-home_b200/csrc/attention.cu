@@ -229,7 +229,8 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-__global__ void __maxnreg__(200)
+// (320 threads x 200 registers did not launch (cudaErrorLaunchOutOfResources); the launch-bounds build uses 168)
+__global__ void __launch_bounds__(NUM_THREADS2, 1)
 attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ out, int d_model, int num_heads,
                         float scale_log2e) {
     extern __shared__ uint8_t smem_raw[];
