@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(256, 2) ln_relu_fwd_kernel(
 //   dh   = rstd * (dxh - mean_c(dxh) - xhat * mean_c(dxh * xhat))     dbias += dh
 // ------------------------------------------------------------------------------------------------
 template <int C>
-__global__ void __launch_bounds__(C / 8) ln_relu_bwd_kernel(const bf16* __restrict__ da, const bf16* __restrict__ h,
+__global__ void __launch_bounds__(C / 8, (C <= 2048) ? 2 : 1) ln_relu_bwd_kernel(const bf16* __restrict__ da, const bf16* __restrict__ h,
                                                             const float* __restrict__ mean_in,
                                                             const float* __restrict__ rstd_in,
                                                             const float* __restrict__ gamma,
@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(C / 8) ln_relu_bwd_kernel(const bf16* __restri
     };
     issue_loads(row0);
     for (int rb = row0; rb < row_end; rb += RB) {
-        float gv[RB][8], xh[RB][8], rs[RB];
+        float rs[RB];
         float part[2 * RB];
         int4 qa_c[RB], qh_c[RB];
         float mu_c[RB];
@@ -223,29 +223,33 @@ __global__ void __launch_bounds__(C / 8) ln_relu_bwd_kernel(const bf16* __restri
             rs[r] = nrs[r];
         }
         if (rb + RB < row_end) issue_loads(rb + RB);
-#pragma unroll
-        for (int r = 0; r < RB; ++r) {
-            const int row = rb + r;
-            const bool ok = row < row_end;
-            const int4 qa = qa_c[r];
-            const int4 qh = qh_c[r];
-            const float mu = mu_c[r];
-            const uint32_t wa[4] = {(uint32_t)qa.x, (uint32_t)qa.y, (uint32_t)qa.z, (uint32_t)qa.w};
-            const uint32_t wh[4] = {(uint32_t)qh.x, (uint32_t)qh.y, (uint32_t)qh.z, (uint32_t)qh.w};
-            float s1 = 0.f, s2 = 0.f;
+        // masked gradient g and xhat of one (row, 8 columns) slice, from the PACKED inputs: phase 2 recomputes them
+        // instead of keeping 16 floats per row alive across the block reduction (214 -> <= 128 registers: 2 CTAs / SM)
+        auto slice = [&](int r, bool ok, float (&gvv)[8], float (&xhh)[8]) {
+            const uint32_t wa[4] = {(uint32_t)qa_c[r].x, (uint32_t)qa_c[r].y, (uint32_t)qa_c[r].z, (uint32_t)qa_c[r].w};
+            const uint32_t wh[4] = {(uint32_t)qh_c[r].x, (uint32_t)qh_c[r].y, (uint32_t)qh_c[r].z, (uint32_t)qh_c[r].w};
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
                 const float2 fa = unpack_bf16x2(wa[t]);
                 const float2 fh = unpack_bf16x2(wh[t]);
-                const float x0 = (fh.x - mu) * rs[r], x1 = (fh.y - mu) * rs[r];
+                const float x0 = (fh.x - mu_c[r]) * rs[r], x1 = (fh.y - mu_c[r]) * rs[r];
                 const float y0 = x0 * gam[2 * t] + bet[2 * t], y1 = x1 * gam[2 * t + 1] + bet[2 * t + 1];
-                const float g0 = (ok && (!relu || y0 > 0.f)) ? fa.x : 0.f;
-                const float g1 = (ok && (!relu || y1 > 0.f)) ? fa.y : 0.f;
-                gv[r][2 * t] = g0; gv[r][2 * t + 1] = g1;
-                xh[r][2 * t] = x0; xh[r][2 * t + 1] = x1;
-                const float d0 = g0 * gam[2 * t], d1 = g1 * gam[2 * t + 1];
-                s1 += d0 + d1;
-                s2 += d0 * x0 + d1 * x1;
+                gvv[2 * t] = (ok && (!relu || y0 > 0.f)) ? fa.x : 0.f;
+                gvv[2 * t + 1] = (ok && (!relu || y1 > 0.f)) ? fa.y : 0.f;
+                xhh[2 * t] = x0;
+                xhh[2 * t + 1] = x1;
+            }
+        };
+#pragma unroll
+        for (int r = 0; r < RB; ++r) {
+            float gvv[8], xhh[8];
+            slice(r, rb + r < row_end, gvv, xhh);
+            float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                const float d = gvv[t] * gam[t];
+                s1 += d;
+                s2 += d * xhh[t];
             }
             part[2 * r] = s1;
             part[2 * r + 1] = s2;
@@ -268,13 +272,15 @@ __global__ void __launch_bounds__(C / 8) ln_relu_bwd_kernel(const bf16* __restri
         for (int r = 0; r < RB; ++r) {
             const int row = rb + r;
             if (row >= row_end) continue;
+            float gvv[8], xhh[8];
+            slice(r, true, gvv, xhh);
             const float m1 = tot[2 * r], m2 = tot[2 * r + 1];
             float o[8];
 #pragma unroll
             for (int t = 0; t < 8; ++t) {
-                o[t] = rs[r] * (gv[r][t] * gam[t] - m1 - xh[r][t] * m2);
-                acc_db[t] += gv[r][t];
-                acc_dg[t] += gv[r][t] * xh[r][t];
+                o[t] = rs[r] * (gvv[t] * gam[t] - m1 - xhh[t] * m2);
+                acc_db[t] += gvv[t];
+                acc_dg[t] += gvv[t] * xhh[t];
                 acc_dbias[t] += o[t];
             }
             int4 q;
