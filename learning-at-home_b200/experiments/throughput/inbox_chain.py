@@ -119,11 +119,12 @@ def run(args):
                batch_size=batch, block_type=args.block_type, hid_dim=d, dtype=args.dtype, ok=ok,
                gpu_launches=native.launches(),
                layer_ms=ms / (args.passes * L), tokens_per_layer_call=rows)
-    if rank == 0:
-        print(json.dumps(out), flush=True)
     heap.barrier()
     if world > 1 and dist.is_initialized():
         dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(out), flush=True)
     return out
 
 
