@@ -213,7 +213,8 @@ constexpr int OFF_V2 = OFF_K2 + 2 * TILE_BYTES;
 constexpr int OFF_P2 = OFF_V2 + 2 * TILE_BYTES;           // P_A, P_B
 constexpr int OFF_BAR2 = OFF_P2 + 2 * P_BYTES;
 constexpr int NUM_BARS = 1 + 8 + 8;
-constexpr int SMEM_TOTAL2 = OFF_BAR2 + NUM_BARS * 8 + 16 + 1024;
+constexpr int OFF_XCHG3 = OFF_BAR2 + NUM_BARS * 8 + 16;               // v3: max / sum exchange between row halves
+constexpr int SMEM_TOTAL2 = OFF_XCHG3 + 2 * 2 * 2 * Q_TILE * 4 + 1024;
 constexpr int COL_S = 0, COL_O = 256;
 
 __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
@@ -450,6 +451,235 @@ attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __rest
     }
 }
 
+// v3: same pipeline, but TWO threads per query row (each owns 64 of the 128 scores of a block): 16 softmax warps instead
+// of 8, i.e. four warps per SM sub-partition to hide the tcgen05.ld / MUFU / barrier latencies that dominate v2 (ncu: XU
+// pipe 34 %, tensor 17 %).  The two halves of a row agree on the block maximum through shared memory + a named barrier
+// per tile group; each keeps its own partial row sum (same reference maximum), summed once in the epilogue.
+constexpr int NUM_THREADS3 = 576;   // 16 softmax warps + MMA warp + TMA warp
+__global__ void __launch_bounds__(NUM_THREADS3, 1)
+attention_fwd_v3_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ out, int d_model, int num_heads,
+                        float scale_log2e) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR2);
+    uint64_t* bar_q = bars;
+    uint64_t* k_full = bars + 1;    // [2]
+    uint64_t* k_empty = bars + 3;   // [2]
+    uint64_t* v_full = bars + 5;    // [2]
+    uint64_t* v_empty = bars + 7;   // [2]
+    uint64_t* s_full = bars + 9;    // [2 tiles]  MMA -> softmax
+    uint64_t* s_free = bars + 11;   // [2 tiles]  softmax (128 threads) -> MMA
+    uint64_t* p_full = bars + 13;   // [2 tiles]  softmax (128 threads) -> MMA
+    uint64_t* pv_done = bars + 15;  // [2 tiles]  MMA -> softmax
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + NUM_BARS);
+    float* xchg = reinterpret_cast<float*>(smem + OFF_XCHG3);   // [2 buffers][2 tiles][2 halves][128 rows]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qpair = blockIdx.x & 1;
+    const int head = (blockIdx.x >> 1) % num_heads;
+    const int batch = (blockIdx.x >> 1) / num_heads;
+    const int seq_row0 = batch * S_LEN;
+
+    if (warp == 17 && lane == 0) {
+        tma_prefetch_desc(&tm_qkv);
+        mbar_init(bar_q, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&k_full[i], 1);
+            mbar_init(&k_empty[i], 1);
+            mbar_init(&v_full[i], 1);
+            mbar_init(&v_empty[i], 1);
+            mbar_init(&s_full[i], 1);
+            mbar_init(&s_free[i], 256);
+            mbar_init(&p_full[i], 256);
+            mbar_init(&pv_done[i], 1);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 16) tmem_alloc(tmem_ptr, 512);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 17) {
+        if (lane == 0) {
+            // ------------------------------------------------------------------ TMA producer
+            mbar_arrive_expect_tx(bar_q, 2 * TILE_BYTES);
+            tma_load_2d(smem + OFF_Q2, &tm_qkv, bar_q, head * HEAD_DIM, seq_row0 + (2 * qpair) * Q_TILE);
+            tma_load_2d(smem + OFF_Q2 + TILE_BYTES, &tm_qkv, bar_q, head * HEAD_DIM, seq_row0 + (2 * qpair + 1) * Q_TILE);
+            for (int j = 0; j < NUM_KB; ++j) {
+                const int st = j & 1;
+                const uint32_t par = ((j >> 1) & 1) ^ 1;
+                mbar_wait(&k_empty[st], par);
+                mbar_arrive_expect_tx(&k_full[st], TILE_BYTES);
+                tma_load_2d(smem + OFF_K2 + st * TILE_BYTES, &tm_qkv, &k_full[st], d_model + head * HEAD_DIM, seq_row0 + j * KB);
+                mbar_wait(&v_empty[st], par);
+                mbar_arrive_expect_tx(&v_full[st], TILE_BYTES);
+                tma_load_2d(smem + OFF_V2 + st * TILE_BYTES, &tm_qkv, &v_full[st], 2 * d_model + head * HEAD_DIM, seq_row0 + j * KB);
+            }
+        }
+    } else if (warp == 16) {
+        if (lane == 0) {
+            // ------------------------------------------------------------------ MMA issuer
+            constexpr uint32_t idesc_s = make_idesc_bf16_f32(Q_TILE, KB, 0u, 0u);
+            constexpr uint32_t idesc_o = make_idesc_bf16_f32(Q_TILE, HEAD_DIM, 0u, 1u);
+            const uint32_t sq = smem_u32(smem + OFF_Q2), sk = smem_u32(smem + OFF_K2), sv = smem_u32(smem + OFF_V2),
+                           sp = smem_u32(smem + OFF_P2);
+            auto issue_s = [&](int t, int j) {
+                const uint32_t a = sq + t * TILE_BYTES, b = sk + (j & 1) * TILE_BYTES;
+#pragma unroll
+                for (int ks = 0; ks < HEAD_DIM / 16; ++ks)
+                    umma_bf16_ss(tmem_base + COL_S + t * KB, make_smem_desc_sw128(a + ks * 32, 0, 1024),
+                                 make_smem_desc_sw128(b + ks * 32, 0, 1024), idesc_s, ks > 0 ? 1u : 0u);
+                umma_commit(&s_full[t]);
+            };
+            mbar_wait(bar_q, 0);
+            mbar_wait(&k_full[0], 0);
+            tcgen05_fence_after();
+            issue_s(0, 0);
+            issue_s(1, 0);
+            umma_commit(&k_empty[0]);
+            for (int j = 0; j < NUM_KB; ++j) {
+                const int st = j & 1;
+                for (int t = 0; t < 2; ++t) {
+                    if (j + 1 < NUM_KB) {   // S of the NEXT block first: the softmax warps hold S_t(j) in registers already
+                        if (t == 0) mbar_wait(&k_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
+                        mbar_wait(&s_free[t], j & 1);
+                        tcgen05_fence_after();
+                        issue_s(t, j + 1);
+                        if (t == 1) umma_commit(&k_empty[(j + 1) & 1]);
+                    }
+                    mbar_wait(&p_full[t], j & 1);
+                    if (t == 0) mbar_wait(&v_full[st], (j >> 1) & 1);
+                    tcgen05_fence_after();
+                    const uint32_t a = sp + t * P_BYTES, b = sv + st * TILE_BYTES;
+#pragma unroll
+                    for (int kb = 0; kb < KB / 64; ++kb) {
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks)
+                            umma_bf16_ss(tmem_base + COL_O + t * HEAD_DIM,
+                                         make_smem_desc_sw128(a + kb * (Q_TILE * 128) + ks * 32, 0, 1024),
+                                         make_smem_desc_sw128(b + (kb * 64 + ks * 16) * 128, 0, 1024), idesc_o,
+                                         (j | kb | ks) ? 1u : 0u);
+                    }
+                    umma_commit(&pv_done[t]);
+                    if (t == 1) umma_commit(&v_empty[st]);
+                }
+            }
+        }
+    } else {
+        // ---------------------------------------------------------------------- softmax + epilogue: 2 threads per query row
+        const int t = warp >> 3;                 // query tile of the pair
+        const int hc = (warp >> 2) & 1;          // which 64 of the 128 scores of a block (and which 32 output columns)
+        const int row = (warp & 3) * 32 + lane;  // row inside the tile == TMEM lane
+        const uint32_t lane_base = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+        const uint32_t ts = lane_base + COL_S + t * KB + hc * 64, to = lane_base + COL_O + t * HEAD_DIM + hc * 32;
+        uint8_t* pbase = smem + OFF_P2 + t * P_BYTES + hc * (Q_TILE * 128);   // P tile of keys [64 hc, 64 hc + 64)
+        float m = -INFINITY, l = 0.f;
+        const float lazy_margin = 8.f / scale_log2e;
+#pragma unroll 1
+        for (int j = 0; j < NUM_KB; ++j) {
+            mbar_wait(&s_full[t], j & 1);
+            tcgen05_fence_after();
+            uint32_t r[2][32];
+            tmem_ld_32x32(ts, r[0]);
+            tmem_ld_32x32(ts + 32, r[1]);
+            tmem_ld_wait();
+            tcgen05_fence_before();
+            mbar_arrive(&s_free[t]);
+            float mxs8[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) mxs8[i] = -INFINITY;
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+#pragma unroll
+                for (int i = 0; i < 32; ++i) mxs8[i & 7] = fmaxf(mxs8[i & 7], __uint_as_float(r[c][i]));
+            float mx = fmaxf(fmaxf(fmaxf(mxs8[0], mxs8[1]), fmaxf(mxs8[2], mxs8[3])),
+                             fmaxf(fmaxf(mxs8[4], mxs8[5]), fmaxf(mxs8[6], mxs8[7])));
+            // agree on the block maximum of the row with the thread that owns the other 64 scores
+            float* xb = xchg + (((j & 1) * 2 + t) * 2) * Q_TILE;
+            xb[hc * Q_TILE + row] = mx;
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + t), "r"(256) : "memory");
+            mx = fmaxf(mx, xb[(hc ^ 1) * Q_TILE + row]);
+            float alpha = 1.f;
+            if (mx > m + lazy_margin || j == 0) {
+                alpha = exp2f((m - mx) * scale_log2e);
+                m = mx;
+            }
+            const float ms = m * scale_log2e;
+            if (j > 0) {
+                mbar_wait(&pv_done[t], (j - 1) & 1);
+                tcgen05_fence_after();
+                if (__any_sync(0xffffffffu, alpha != 1.f)) {   // my 32 columns of the running output
+                    uint32_t o[32];
+                    tmem_ld_32x32(to, o);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                    tmem_st_32x32(to, o);
+                    tmem_st_wait();
+                }
+            }
+            float sum4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                uint32_t packed[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const float p0 = exp2f(__uint_as_float(r[c][2 * i]) * scale_log2e - ms);
+                    const float p1 = exp2f(__uint_as_float(r[c][2 * i + 1]) * scale_log2e - ms);
+                    const uint32_t pk = pack_bf16x2(p0, p1);
+                    const float2 back = unpack_bf16x2(pk);
+                    sum4[i & 3] += back.x + back.y;
+                    packed[i] = pk;
+                }
+                uint8_t* tile_row = pbase + row * 128;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int chunk = c * 4 + q;
+                    int4 v;
+                    v.x = packed[4 * q + 0]; v.y = packed[4 * q + 1]; v.z = packed[4 * q + 2]; v.w = packed[4 * q + 3];
+                    *reinterpret_cast<int4*>(tile_row + ((chunk ^ (row & 7)) << 4)) = v;
+                }
+            }
+            l = l * alpha + ((sum4[0] + sum4[1]) + (sum4[2] + sum4[3]));
+            tcgen05_fence_before();
+            fence_proxy_async_smem();
+            mbar_arrive(&p_full[t]);
+        }
+        // total row sum = the two partial sums (same reference maximum m)
+        float* xb = xchg + ((0 * 2 + t) * 2) * Q_TILE;   // buffer 0 was last used by block NUM_KB - 2: free again
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + t), "r"(256) : "memory");
+        xb[hc * Q_TILE + row] = l;
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + t), "r"(256) : "memory");
+        l += xb[(hc ^ 1) * Q_TILE + row];
+        mbar_wait(&pv_done[t], (NUM_KB - 1) & 1);
+        tcgen05_fence_after();
+        const float inv = 1.f / l;
+        bf16* op = out + static_cast<long long>(seq_row0 + (2 * qpair + t) * Q_TILE + row) * d_model + head * HEAD_DIM + hc * 32;
+        {
+            uint32_t r[32];
+            tmem_ld_32x32(to, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                int4 v;
+                v.x = pack_bf16x2(__uint_as_float(r[8 * i + 0]) * inv, __uint_as_float(r[8 * i + 1]) * inv);
+                v.y = pack_bf16x2(__uint_as_float(r[8 * i + 2]) * inv, __uint_as_float(r[8 * i + 3]) * inv);
+                v.z = pack_bf16x2(__uint_as_float(r[8 * i + 4]) * inv, __uint_as_float(r[8 * i + 5]) * inv);
+                v.w = pack_bf16x2(__uint_as_float(r[8 * i + 6]) * inv, __uint_as_float(r[8 * i + 7]) * inv);
+                *reinterpret_cast<int4*>(op + 8 * i) = v;
+            }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 16) {
+        tcgen05_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
 }  // namespace v2
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -485,14 +715,18 @@ int lah_attention_fwd(const void* qkv, void* out, int batch, int num_heads, int 
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return -1000 - (int)r;
     static bool configured = false;
-    static int use_v1 = 0;
+    static int use_v1 = 0, use_version = 2;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
         if (e != cudaSuccess) return -(int)e;
         e = cudaFuncSetAttribute(v2::attention_fwd_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::SMEM_TOTAL2);
         if (e != cudaSuccess) return -(int)e;
-        const char* env = getenv("LAH_ATTN_V1");   // A/B switch: the one-tile-per-CTA kernel
+        e = cudaFuncSetAttribute(v2::attention_fwd_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::SMEM_TOTAL2);
+        if (e != cudaSuccess) return -(int)e;
+        const char* env = getenv("LAH_ATTN_V1");   // A/B switches: LAH_ATTN_V1=1 one tile per CTA; LAH_ATTN=3 two threads / row
         use_v1 = env && atoi(env) == 1;
+        env = getenv("LAH_ATTN");
+        if (env) use_version = atoi(env);
         configured = true;
     }
     if (batch <= 0) return 0;
@@ -500,6 +734,9 @@ int lah_attention_fwd(const void* qkv, void* out, int batch, int num_heads, int 
     if (use_v1)
         attention_fwd_kernel<<<batch * num_heads * (S_LEN / Q_TILE), NUM_THREADS, SMEM_TOTAL, st>>>(tm, (bf16*)out, d_model,
                                                                                               num_heads, scale_log2e);
+    else if (use_version == 3)
+        v2::attention_fwd_v3_kernel<<<batch * num_heads * 2, v2::NUM_THREADS3, v2::SMEM_TOTAL2, st>>>(
+            tm, (bf16*)out, d_model, num_heads, scale_log2e);
     else
         v2::attention_fwd_v2_kernel<<<batch * num_heads * 2, v2::NUM_THREADS2, v2::SMEM_TOTAL2, st>>>(
             tm, (bf16*)out, d_model, num_heads, scale_log2e);
