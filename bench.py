@@ -112,6 +112,12 @@ def dist_setup(n_gpus):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if torch.cuda.is_available():
         torch.cuda.set_device(local_rank)
+        try:  # run next to the GPU: the pinned staging buffers of the end-to-end path are placed by first touch
+            import lah_b200  # noqa
+            from lah_b200.utils.affinity import bind_to_gpu_numa_node
+            bind_to_gpu_numa_node(local_rank)
+        except Exception:
+            pass
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl" if torch.cuda.is_available() else "gloo",
