@@ -227,8 +227,11 @@ def test_metrics_log_and_stage_timer(tmp_path):
     trainer = DMoETrainer(cfg, device="cpu", metrics_path=str(path))
     x, y = torch.randn(16, 8), torch.randint(0, 10, (16,))
     loss = trainer.train_step(x, y)
+    handle = trainer.train_step_async(x, y, prefetch=(x, y))   # same API as on the GPU (there it returns before the step ran)
+    assert isinstance(handle.result(), float) and handle.result() == handle.result()
+    loss = handle.result()
     rec = trainer.log_step(loss=loss, samples=16, step_ms=2.0, note="cpu")
-    assert rec["samples_per_s"] == 8000.0 and rec["step"] == 1
+    assert rec["samples_per_s"] == 8000.0 and rec["step"] == 2
     trainer.metrics.close()
     lines = [json.loads(l) for l in open(path)]
     assert len(lines) == 1 and lines[0]["note"] == "cpu" and abs(lines[0]["loss"] - loss) < 1e-6
