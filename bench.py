@@ -46,6 +46,8 @@ def parse_args():
                     help="receive-buffer rows / local (token, expert) pairs; 0 = auto (retry with a larger one on overflow)")
     ap.add_argument("--shadow-experts", type=int, default=8,
                     help="max hot experts per layer and step that are processed data-parallel on every rank (0 = static placement)")
+    ap.add_argument("--shadow-tol", type=float, default=1.1,
+                    help="shadow selection stops once the most loaded rank is within this factor of the mean load")
     ap.add_argument("--expert-dtype", choices=["bf16", "fp8"], default="bf16",
                     help="fp8 = forward expert GEMMs on block-scaled FP8 tensor cores (MXFP8)")
     ap.add_argument("--no-e2e", action="store_true")
@@ -205,7 +207,8 @@ def _measure_ours(args, rank, world, local_rank, B, capacity_factor):
     from lah_b200.parallel.trainer import DMoETrainer
     cfg = DMoEConfig(hidden=args.hidden, grid_size=tuple(args.grid), k=args.k, num_layers=args.layers,
                      tokens_per_rank=B, capacity_factor=capacity_factor, failure_rate=args.failure_rate,
-                     gate_mode=args.gate, shadow_experts=args.shadow_experts, expert_dtype=args.expert_dtype)
+                     gate_mode=args.gate, shadow_experts=args.shadow_experts, shadow_tol=args.shadow_tol,
+                     expert_dtype=args.expert_dtype)
     trainer = DMoETrainer(cfg)
     gen = torch.Generator().manual_seed(1234 + rank)
     n_batches = 4
@@ -308,7 +311,7 @@ def _measure_ours(args, rank, world, local_rank, B, capacity_factor):
                                 f"FeedforwardBlock({cfg.hidden}), top-{cfg.k}] -> LayerNorm -> Linear({cfg.hidden},10); "
                                 "fwd+bwd+per-expert AMSGrad+trainer AMSGrad",
                        "global_batch": global_batch, "seq_len": 1, "parallelism": f"ep{world}+dp{world}",
-                       "capacity_factor": capacity_factor, "shadow_experts": cfg.shadow_experts if world > 1 else 0,
+                       "capacity_factor": capacity_factor, "shadow_experts": cfg.shadow_experts if world > 1 else 0, "shadow_tol": cfg.shadow_tol,
                        "expert_gemm_dtype": cfg.expert_dtype + (" forward, bf16 dgrad/wgrad" if cfg.expert_dtype == "fp8" else ""),
                        "experts_total": cfg.num_experts * cfg.num_layers, "failure_rate": cfg.failure_rate,
                        "gate": cfg.gate_mode + (" (LayerNorm(x) @ normalize(keys); gate params not trained, exactly like the reference's EmulatedDMoE)" if cfg.gate_mode == "emulator" else " (trainable product-key proj, lib.GatingFunction)"),
