@@ -235,3 +235,25 @@ def test_metrics_log_and_stage_timer(tmp_path):
     trainer.metrics.close()
     lines = [json.loads(l) for l in open(path)]
     assert len(lines) == 1 and lines[0]["note"] == "cpu" and abs(lines[0]["loss"] - loss) < 1e-6
+
+
+def test_shadow_plan_balances_skewed_routing():
+    """host model of the kernel's hot-expert selection: never makes the worst rank worse, stops when balanced"""
+    from lah_b200.parallel.balance import rank_loads, shadow_plan
+    gen = torch.Generator().manual_seed(0)
+    world, E, E_loc = 8, 64, 8
+    # heavy skew: 4 experts take ~85 % of the rows, tokens are i.i.d. across ranks
+    probs = torch.full((E,), 0.15 / (E - 4))
+    probs[torch.tensor([3, 17, 18, 60])] = 0.85 / 4
+    counts = [torch.multinomial(probs, 20000, replacement=True, generator=gen).bincount(minlength=E).tolist() for _ in range(world)]
+    before = rank_loads(counts, E_loc)
+    shadowed, after = shadow_plan(counts, E_loc, max_shadow=8, tol=1.1, min_rows=64)
+    mean = sum(before) / world
+    assert sum(after) == sum(before)
+    assert max(before) / mean > 2.5 and max(after) / mean <= 1.1
+    assert set(shadowed[:4]) == {3, 17, 18, 60} or set(shadowed) >= {3, 17, 18, 60}
+    # balanced routing: nothing is shadowed
+    uniform = [[100] * E for _ in range(world)]
+    assert shadow_plan(uniform, E_loc, 8)[0] == []
+    # single rank: never shadows
+    assert shadow_plan([counts[0]], E, 8)[0] == []

@@ -38,6 +38,12 @@ def main():
     torch.cuda.synchronize()
     ctx.check_status()
     shadowed = int((layer.ws.shadow_info.view(-1, 4)[:, 0] >= 0).sum())
+    # the kernel's hot-expert selection must equal the host model (parallel/balance.py) on the exchanged count table
+    from lah_b200.parallel.balance import shadow_plan
+    counts = ctx.cnt_all[:world].cpu().tolist()
+    plan, _ = shadow_plan(counts, ctx.E_loc, ctx.S, tol=cfg.shadow_tol, min_rows=cfg.shadow_min_rows)
+    got = [int(e) for e in layer.ws.shadow_info.view(-1, 4)[:, 0].cpu().tolist() if e >= 0]
+    plan_ok = plan == got
     # gather what the distributed run produced
     ys = [torch.empty_like(y) for _ in range(world)]
     dxs = [torch.empty_like(x.grad) for _ in range(world)]
@@ -70,8 +76,9 @@ def main():
                     b2_max_abs=(torch.cat(b2s) - ref.shard.views["b2"]).abs().max().item(),
                     steps=bool((torch.cat(steps).cpu() == ref.shard.step.cpu()).all()))
         ok = errs["y"] < 2e-2 and errs["dx"] < 3e-2 and errs["dproj"] < 5e-2 and errs["w1_mean_abs"] < 1e-4 and errs["b2_max_abs"] < 2.5e-3 and errs["steps"]
-        ok = ok and (shadowed > 0 or not force_shadow)
-        print("multi_gpu_check", dict(force_shadow=force_shadow, shadowed_experts=shadowed), errs, flush=True)
+        ok = ok and (shadowed > 0 or not force_shadow) and plan_ok
+        print("multi_gpu_check", dict(force_shadow=force_shadow, shadowed_experts=shadowed, plan_matches_host_model=plan_ok,
+                                      plan=plan, kernel=got), errs, flush=True)
         print("MULTI_GPU_OK" if ok else "MULTI_GPU_FAILED", flush=True)
     dist.barrier()
     dist.destroy_process_group()
