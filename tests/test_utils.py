@@ -157,3 +157,16 @@ def test_shared_arrays():
 def test_check_numpy():
     t = torch.arange(3.0, requires_grad=True)
     assert isinstance(utils.check_numpy(t), np.ndarray) and utils.check_numpy([1, 2]).shape == (2,)
+
+
+def test_lib_alias_exposes_the_reference_public_surface():
+    """`import lib` (README snippets / experiment scripts of the reference) resolves every public name of SURVEY.md §1"""
+    import lib
+    names = ("RemoteExpert GatingFunction TesseractServer TesseractNetwork ExpertBackend TesseractRuntime TaskPool "
+             "BatchTensorProto TensorProto ArrayProto Connection PytorchSerializer PickleSerializer nested_compare "
+             "nested_flatten nested_pack nested_map SharedArrays SharedArray SharedFuture run_in_background repeated "
+             "CountdownEvent await_first run_and_await_k check_numpy DUMMY DUMMY_BATCH_SIZE").split()
+    assert [n for n in names if not hasattr(lib, n)] == []
+    assert lib.server.TesseractServer is lib.TesseractServer and lib.client.RemoteExpert is lib.RemoteExpert
+    assert lib.network.HEARTBEAT_EXPIRATION == 120 and lib.network.UID_DELIMETER == "."
+    assert lib.Connection.header_size == 4 and lib.Connection.payload_length_size == 8 and lib.DUMMY_BATCH_SIZE == 3
