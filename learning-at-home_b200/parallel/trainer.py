@@ -217,6 +217,8 @@ class DMoETrainer:
 
     @torch.no_grad()
     def evaluate(self, x: torch.Tensor, y: torch.Tensor):
+        """loss / accuracy of one batch.  COLLECTIVE on multi-GPU runs: the experts are sharded over the ranks, so every
+        rank must call it at the same point (with its own batch of at most ``tokens_per_rank`` rows)."""
         self.model.eval()
         logits = self.model(x.to(self.device))
         y = y.to(self.device)
