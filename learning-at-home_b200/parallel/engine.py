@@ -150,6 +150,12 @@ class EngineContext:
         self.dh = torch.empty(self.max_rows, cfg.inner, **bf)
         self.heap.barrier()
 
+    def close(self):
+        """release the symmetric heap (peer mappings + the arena); idempotent.  All tensors carved out of the heap become
+        invalid, so call it only when the trainer / layers of this context are no longer used."""
+        K.set_wait_counter(None)
+        self.heap.close()
+
     def next_epoch(self) -> int:
         self.epoch += 1
         return self.epoch

@@ -72,6 +72,20 @@ class DMoETrainer:
             self._slot = 0
             self._loss_host = [torch.empty(1, dtype=torch.float32).pin_memory() for _ in range(2)]
 
+    def close(self):
+        """flush the metrics log and release the peer-mapped symmetric heap (GPU runs); idempotent"""
+        self.metrics.close()
+        if self.cuda and self.ctx is not None:
+            torch.cuda.synchronize(self.device)
+            self.ctx.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
+
     # ------------------------------------------------------------------ trainer-side flat parameters
     def _flatten_trainer_params(self):
         params = [p for p in self.model.parameters() if p.requires_grad]  # a frozen (emulator-style) gate stays out
