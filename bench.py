@@ -32,7 +32,9 @@ def parse_args():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--impl", choices=["ours", "reference", "baseline"], default="ours",
+                    help="baseline = the same step written with torch.topk + NCCL all_to_all_single + cuBLAS + torch Adam "
+                         "(lah_b200/parallel/baseline.py): 'the baseline, not the product'")
     ap.add_argument("--batch-per-gpu", type=int, default=65536, help="samples per GPU per step (weak scaling)")
     ap.add_argument("--ref-batch", type=int, default=64, help="samples per step for the reference arm")
     ap.add_argument("--hidden", type=int, default=512)
@@ -324,6 +326,59 @@ def _measure_ours(args, rank, world, local_rank, B, capacity_factor):
     return True
 
 
+# ------------------------------------------------------------------------------------------------ NCCL + cuBLAS baseline
+def run_baseline(args):
+    """same model / step through parallel/baseline.py: product-key gate, index_select permute, all_to_all_single (NCCL),
+    per-expert F.linear under bf16 autocast (cuBLAS), one torch Adam(amsgrad) per expert"""
+    rank, world, local_rank = dist_setup(args.gpus)
+    cuda = torch.cuda.is_available()
+    if not cuda and not os.environ.get("LAH_BENCH_ALLOW_CPU"):
+        print(json.dumps({"impl": "baseline", "unavailable": "no CUDA device visible"}))
+        return
+    import lah_b200  # noqa
+    from lah_b200.parallel.engine import DMoEConfig
+    from lah_b200.parallel.baseline import BaselineTrainer
+    B = args.batch_per_gpu
+    grid = tuple(args.grid) if len(args.grid) > 1 else (8, 8) if args.grid == [64] else tuple(args.grid)
+    cfg = DMoEConfig(hidden=args.hidden, grid_size=grid, k=args.k, num_layers=args.layers, tokens_per_rank=B,
+                     failure_rate=args.failure_rate, gate_mode="product_key")
+    trainer = BaselineTrainer(cfg, dtype=torch.bfloat16 if cuda else torch.float32)
+    gen = torch.Generator().manual_seed(1234 + rank)
+    dev = trainer.device
+    xs = [torch.randn(B, cfg.in_features, generator=gen).to(dev) for _ in range(2)]
+    ys = [torch.randint(0, cfg.num_classes, (B,), generator=gen).to(dev) for _ in range(2)]
+
+    def step(i):
+        trainer.train_step_device(xs[i % 2], ys[i % 2])
+
+    for i in range(args.warmup):
+        step(i)
+    if cuda:
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        ms = timed(step, args.steps, world)
+        clocks = sampler.stop()
+    else:  # CPU smoke path of this arm (tests)
+        t0 = time.time()
+        for i in range(args.steps):
+            step(i)
+        ms, clocks = (time.time() - t0) * 1e3, {}
+    value = B * world * args.steps / (ms / 1e3)
+    if rank == 0:
+        print(json.dumps({
+            "metric": "DMoE training samples/sec (whole job, device-timed, max over ranks)", "impl": "baseline",
+            "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": value / 16.8,
+            "dtype": "bf16 autocast" if cuda else "fp32", "data": "synthetic (MNIST-shaped 784-d fp32 rows, random-init weights)",
+            "config": {"model": f"same model through torch.topk + all_to_all_single + cuBLAS + torch Adam; grid {grid}",
+                       "global_batch": B * world, "seq_len": 1, "parallelism": f"ep{world}+dp{world} (NCCL all_to_all_single)"},
+            "clocks": clocks, "gpu_launches": 0}))
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 # ------------------------------------------------------------------------------------------------ reference arm
 def run_reference(args):
     ref_root = os.path.join(ROOT, "baseline", "_ref")
@@ -369,7 +424,9 @@ def run_reference(args):
 
 if __name__ == "__main__":
     a = parse_args()
-    if a.impl == "reference":
+    if a.impl == "baseline":
+        run_baseline(a)
+    elif a.impl == "reference":
         try:
             run_reference(a)
         except Exception as e:  # the reference arm must never fail the driver
