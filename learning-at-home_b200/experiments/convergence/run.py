@@ -169,6 +169,8 @@ def run_engine(args, data, printer):
     elapsed = time.time() - t0
     result = dict(train_history=train_history, val_history=val_history, updates_per_sec=steps / elapsed,
                   samples_per_sec=steps * batch / elapsed)
+    printer(f"{steps} fused steps ({steps * args.num_trainers} trainer updates) in {elapsed:.1f}s = "
+            f"{result['samples_per_sec']:.1f} samples/s")
     save_history(args, result)
     return result
 

@@ -305,26 +305,28 @@ def adam_step_ref(p, g, m, v, vmax, seg_sizes, G, *, step, group_rows=None, lr=1
         seg_sizes = [seg_sizes]
     off = 0
     active = torch.ones(G, dtype=torch.bool, device=p.device) if group_rows is None else (group_rows > 0)
-    stepf = step.to(torch.float32).clamp(min=1)
-    bc1 = (1 - betas[0] ** stepf).view(G, 1)
-    bc2 = (1 - betas[1] ** stepf).view(G, 1)
+    idx = active.nonzero().squeeze(1)          # only the active groups are touched (inactive experts are not stepped)
+    stepf = step.to(torch.float32).clamp(min=1)[idx]
+    bc1 = (1 - betas[0] ** stepf).view(-1, 1)
+    bc2 = (1 - betas[1] ** stepf).view(-1, 1)
     for s, size in enumerate(seg_sizes):
         sl = slice(off, off + size * G)
+        off += size * G
+        if idx.numel() == 0:
+            continue
         P, Gr, M, V = p[sl].view(G, size), g[sl].view(G, size), m[sl].view(G, size), v[sl].view(G, size)
-        act = active.view(G, 1)
-        m_new = M + (1 - betas[0]) * (Gr - M)
-        v_new = V * betas[1] + (1 - betas[1]) * Gr * Gr
+        grad = Gr[idx]
+        m_new = M[idx] + (1 - betas[0]) * (grad - M[idx])
+        v_new = V[idx] * betas[1] + (1 - betas[1]) * grad * grad
         if amsgrad:
             VM = vmax[sl].view(G, size)
-            vm_new = torch.maximum(VM, v_new)
+            vm_new = torch.maximum(VM[idx], v_new)
             denom = vm_new.sqrt() / bc2.sqrt() + eps
-            VM.copy_(torch.where(act, vm_new, VM))
+            VM[idx] = vm_new
         else:
             denom = v_new.sqrt() / bc2.sqrt() + eps
-        p_new = P - (lr / bc1) * (m_new / denom)
-        P.copy_(torch.where(act, p_new, P))
-        M.copy_(torch.where(act, m_new, M))
-        V.copy_(torch.where(act, v_new, V))
+        P[idx] = P[idx] - (lr / bc1) * (m_new / denom)
+        M[idx] = m_new
+        V[idx] = v_new
         if (zero_mask >> s) & 1:
-            Gr.copy_(torch.where(act, torch.zeros_like(Gr), Gr))
-        off += size * G
+            Gr[idx] = 0.0

@@ -386,6 +386,7 @@ class FusedDMoE(nn.Module):
         self.shard = ExpertShard(cfg, self.E_loc, self.first_expert, dev, layer_index, ctx=ctx)
         self.ref_fail_mask = None  # tests can inject an explicit failure mask into the oracle path
         self._ref_rows = None
+        self._ref_leaves = {}   # CPU mode: local expert -> {segment: leaf view} of the experts used since the last update
 
     # ------------------------------------------------------------------ public forward
     def forward(self, x):
@@ -532,30 +533,36 @@ class FusedDMoE(nn.Module):
     # ------------------------------------------------------------------ PyTorch oracle (CPU path, tests)
     def _expert_params(self, e_local: int, dtype=torch.float32):
         if self.ctx is None and torch.is_grad_enabled() and self.training:
-            # CPU mode: slice the flat leaf so autograd accumulates expert gradients into shard.p.grad
-            sh = self.shard
-            sh.p.requires_grad_(True)
-            out, off = {}, 0
-            for n, size in zip(SEG_NAMES, sh.seg_sizes):
-                shape = sh.views[n].shape[1:]
-                out[n] = sh.p[off + e_local * size: off + (e_local + 1) * size].view(shape)
-                off += size * sh.slots
-            return out
+            # CPU mode: every parameter of the expert is a LEAF VIEW into the flat buffer (detached, same storage), so
+            # autograd produces one small gradient per tensor; apply_expert_gradients_ref copies them into shard.g.
+            # (Slicing one big leaf instead makes autograd materialise a full-size zero tensor per slice.)
+            leaves = self._ref_leaves.get(e_local)
+            if leaves is None:
+                leaves = {n: self.shard.views[n][e_local].detach().requires_grad_(True) for n in SEG_NAMES}
+                self._ref_leaves[e_local] = leaves
+            return leaves
         return {n: self.shard.views[n][e_local].to(dtype) for n in SEG_NAMES}
 
     def apply_expert_gradients_ref(self):
         """CPU-mode counterpart of apply_expert_gradients (same per-expert AMSGrad rule, PyTorch ops)"""
         sh, cfg = self.shard, self.cfg
-        if sh.p.grad is None or self._ref_rows is None:
+        if self._ref_rows is None:
             return
         rows = self._ref_rows
         sh.step += (rows > 0).to(sh.step.dtype)
         with torch.no_grad():
-            K.adam_step_ref(sh.p, sh.p.grad, sh.m, sh.v, sh.vmax, sh.seg_sizes, self.E_loc, step=sh.step,
+            for le, leaves in self._ref_leaves.items():   # gather the per-tensor gradients into the flat gradient buffer
+                for n, leaf in leaves.items():
+                    if leaf.grad is not None:
+                        sh.grads[n][le].copy_(leaf.grad)
+                        leaf.grad = None
+                    else:
+                        sh.grads[n][le].zero_()
+            K.adam_step_ref(sh.p, sh.g, sh.m, sh.v, sh.vmax, sh.seg_sizes, self.E_loc, step=sh.step,
                             group_rows=rows, lr=cfg.lr, betas=cfg.betas, eps=cfg.eps, amsgrad=cfg.amsgrad)
-            sh.p.grad = None
         sh.sync_bf16()
         self._ref_rows = None
+        self._ref_leaves = {}
 
     def _forward_ref(self, x, logits, emulate_bf16: bool = False):
         """Dense reference of the layer: same routing, fp32 expert maths, differentiable w.r.t. x and logits only
