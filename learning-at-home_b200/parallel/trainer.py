@@ -229,6 +229,28 @@ class DMoETrainer:
         done.record(stream)
         return PendingLoss(event=done, host=host)
 
+    # ------------------------------------------------------------------ liveness (failure detection / emulation)
+    @torch.no_grad()
+    def set_alive(self, alive) -> None:
+        """Install the expert liveness table the gate reads: ``alive`` is a bool / 0-1 tensor of ``num_experts`` entries
+        (shared by all DMoE layers, like one DHT) — e.g. ``InBoxNetwork.alive_mask(grid, prefix)`` after heartbeats expired.
+        Dead experts are never selected; the softmax renormalises over the survivors (gating_function.py:55-57)."""
+        alive = torch.as_tensor(alive).to(torch.uint8).reshape(-1)
+        assert alive.numel() == self.cfg.num_experts
+        if self.cuda:
+            self.ctx.alive.copy_(alive.to(self.device))
+        else:
+            for block in self.model.blocks:
+                block.alive_ref = alive.clone()
+
+    def mark_rank_dead(self, rank: int, world: Optional[int] = None) -> None:
+        """emulate the loss of one GPU: every expert it hosts disappears from the routing tables of all trainers"""
+        world = world or self.world
+        e_loc = self.cfg.num_experts // world
+        alive = torch.ones(self.cfg.num_experts, dtype=torch.uint8)
+        alive[rank * e_loc: (rank + 1) * e_loc] = 0
+        self.set_alive(alive)
+
     @torch.no_grad()
     def evaluate(self, x: torch.Tensor, y: torch.Tensor):
         """loss / accuracy of one batch.  COLLECTIVE on multi-GPU runs: the experts are sharded over the ranks, so every

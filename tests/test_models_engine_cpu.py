@@ -257,3 +257,21 @@ def test_shadow_plan_balances_skewed_routing():
     assert shadow_plan(uniform, E_loc, 8)[0] == []
     # single rank: never shadows
     assert shadow_plan([counts[0]], E, 8)[0] == []
+
+
+def test_dead_experts_are_never_routed_to():
+    """liveness table (the in-box DHT): experts of a 'dead rank' disappear from the routing, training continues"""
+    from lah_b200.parallel.engine import DMoEConfig
+    from lah_b200.parallel.trainer import DMoETrainer
+    cfg = DMoEConfig(hidden=32, grid_size=(4, 4), k=4, num_layers=2, in_features=8, tokens_per_rank=64)
+    trainer = DMoETrainer(cfg, device="cpu")
+    x, y = torch.randn(64, 8), torch.randint(0, 10, (64,))
+    trainer.train_step(x, y)
+    steps_before = [b.shard.step.clone() for b in trainer.model.blocks]
+    trainer.mark_rank_dead(1, world=4)          # experts 4..7 vanish
+    for _ in range(3):
+        loss = trainer.train_step(x, y)
+    assert loss == loss
+    for before, block in zip(steps_before, trainer.model.blocks):
+        delta = block.shard.step - before
+        assert int(delta[4:8].sum()) == 0 and int(delta.sum()) > 0   # dead experts received no rows, hence no optimizer steps
