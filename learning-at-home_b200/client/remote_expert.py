@@ -12,6 +12,7 @@ import torch
 import torch.nn as nn
 
 from ..utils import Connection, DUMMY, PytorchSerializer, nested_compare, nested_flatten, nested_pack
+from ..utils import tensor_wire
 
 
 class RemoteExpertError(RuntimeError):
@@ -25,6 +26,24 @@ def _call(host: str, port: int, header: str, payload, timeout=None):
         connection.send_raw(header, PytorchSerializer.dumps(payload))
         reply_header, message = connection.recv_message()
     result = PytorchSerializer.loads(message)
+    if reply_header == "err_":
+        raise RemoteExpertError(f"{header.strip('_')} on {host}:{port} failed on the server: {result}")
+    return result
+
+
+def _call_tensors(host: str, port: int, header: str, uid: str, tensors, timeout=None, fast: bool = False):
+    """'fwd_' / 'bwd_' request; with ``fast`` the negotiated raw-tensor frames are used (no torch.save on either side)"""
+    if not (fast and tensor_wire.supported(tensors)):
+        return _call(host, port, header, (uid, tuple(tensors)), timeout)
+    fast_header = {"fwd_": "fwdT", "bwd_": "bwdT"}[header]
+    with Connection.create(host, port, timeout=timeout) as connection:
+        if timeout is not None:
+            connection.conn.settimeout(timeout)
+        connection.send_parts(fast_header, *tensor_wire.encode(uid, tensors))
+        reply_header = connection.recv_header()
+        if reply_header == tensor_wire.REPLY_HEADER:
+            return tensor_wire.decode(connection.recv_buffer())[1]
+        result = PytorchSerializer.loads(connection.recv_raw())
     if reply_header == "err_":
         raise RemoteExpertError(f"{header.strip('_')} on {host}:{port} failed on the server: {result}")
     return result
@@ -49,7 +68,8 @@ class RemoteExpert(nn.Module):
         forward_inputs = (args, kwargs)
         if not nested_compare(forward_inputs, info["forward_schema"]):
             raise TypeError("Inputs do not match expert input schema. Did you pass the right number of parameters?")
-        flat_outputs = _RemoteModuleCall.apply(DUMMY, self.uid, self.host, self.port, self.timeout,
+        fast = bool(info.get("tensor_wire"))   # only servers of this package advertise the raw-tensor extension
+        flat_outputs = _RemoteModuleCall.apply(DUMMY, self.uid, self.host, self.port, (self.timeout, fast),
                                                *nested_flatten(forward_inputs))
         return nested_pack(flat_outputs, structure=info["outputs_schema"])
 
@@ -77,9 +97,10 @@ class _RemoteModuleCall(torch.autograd.Function):
     @staticmethod
     def forward(ctx, dummy, uid, host, port, timeout, *inputs):
         inputs = tuple(t.detach() for t in inputs)
-        ctx.uid, ctx.host, ctx.port, ctx.timeout = uid, host, port, timeout
+        timeout, fast = timeout if isinstance(timeout, tuple) else (timeout, False)
+        ctx.uid, ctx.host, ctx.port, ctx.timeout, ctx.fast = uid, host, port, timeout, fast
         ctx.save_for_backward(*inputs)
-        outputs = _call(host, port, "fwd_", (uid, tuple(t.cpu() for t in inputs)), timeout)
+        outputs = _call_tensors(host, port, "fwd_", uid, tuple(t.cpu() for t in inputs), timeout, fast)
         device = inputs[0].device if inputs else torch.device("cpu")
         return tuple(t.to(device) for t in outputs)
 
@@ -87,6 +108,6 @@ class _RemoteModuleCall(torch.autograd.Function):
     def backward(ctx, *grad_outputs) -> Tuple[Optional[torch.Tensor], ...]:
         inputs = ctx.saved_tensors
         payload = tuple(t.detach().cpu() for t in nested_flatten((inputs, grad_outputs)))
-        grad_inputs = _call(ctx.host, ctx.port, "bwd_", (ctx.uid, payload), ctx.timeout)
+        grad_inputs = _call_tensors(ctx.host, ctx.port, "bwd_", ctx.uid, payload, ctx.timeout, ctx.fast)
         device = inputs[0].device if inputs else torch.device("cpu")
         return (DUMMY, None, None, None, None, *(g.to(device) for g in grad_inputs))

@@ -84,8 +84,9 @@ class ExpertBackend(nn.Module):
         return self.forward_pool, self.backward_pool
 
     def get_info(self) -> Dict[str, Any]:
+        # tensor_wire: this server also understands raw-tensor frames (utils/tensor_wire.py); reference clients ignore it
         return dict(forward_schema=self.forward_schema, outputs_schema=self.outputs_schema,
-                    keyword_names=tuple(self.kwargs_schema.keys()))
+                    keyword_names=tuple(self.kwargs_schema.keys()), tensor_wire=1)
 
     # ------------------------------------------------------------------ checkpoints (absent in the reference)
     def checkpoint(self) -> Dict[str, Any]:

@@ -8,15 +8,21 @@ from typing import Dict, Tuple
 
 from ..runtime.expert_backend import ExpertBackend
 from ..utils import Connection, PytorchSerializer
+from ..utils import tensor_wire
 
 
 def handle_connection(connection_tuple: Tuple[socket, str], experts: Dict[str, ExpertBackend], task_timeout=None):
     with Connection(*connection_tuple) as connection:
         try:
             header = connection.recv_header()
-            payload = PytorchSerializer.loads(connection.recv_raw())
-        except (RuntimeError, OSError, EOFError):
-            return  # client went away
+            fast = header in tensor_wire.REQUEST_HEADERS   # raw-tensor frames (negotiated extension, utils/tensor_wire.py)
+            if fast:
+                payload = tensor_wire.decode(connection.recv_buffer())
+                header = tensor_wire.REQUEST_HEADERS[header]
+            else:
+                payload = PytorchSerializer.loads(connection.recv_raw())
+        except (RuntimeError, OSError, EOFError, ValueError):
+            return  # client went away / garbage
         try:
             if header == "fwd_":
                 uid, inputs = payload
@@ -32,6 +38,9 @@ def handle_connection(connection_tuple: Tuple[socket, str], experts: Dict[str, E
         except BaseException as e:  # noqa: delivered to the client
             reply_header, response = "err_", f"{type(e).__name__}: {e}"
         try:
-            connection.send_raw(reply_header, PytorchSerializer.dumps(response))
+            if fast and reply_header == "rest" and tensor_wire.supported(response):
+                connection.send_parts(tensor_wire.REPLY_HEADER, *tensor_wire.encode("", response))
+            else:
+                connection.send_raw(reply_header, PytorchSerializer.dumps(response))
         except (RuntimeError, OSError):
             pass

@@ -48,6 +48,14 @@ class Connection(AbstractContextManager):
             self.conn.sendall(prefix)
             self.conn.sendall(content)
 
+    def send_parts(self, header: str, parts, total_length: int) -> None:
+        """one message whose payload is the concatenation of ``parts`` (bytes / memoryviews), sent without gathering them"""
+        head = header.encode()
+        assert len(head) == self.header_size, f"header must be {self.header_size} ASCII characters"
+        self.conn.sendall(head + total_length.to_bytes(self.payload_length_size, byteorder="big"))
+        for part in parts:
+            self.conn.sendall(part)
+
     # ---------------------------------------------------------------- receive
     def _recv_exact(self, nbytes: int) -> bytearray:
         buf = bytearray(nbytes)
@@ -67,6 +75,11 @@ class Connection(AbstractContextManager):
         """:param max_package: kept for API compatibility with the reference; ignored"""
         length = int.from_bytes(self._recv_exact(self.payload_length_size), byteorder="big")
         return bytes(self._recv_exact(length))
+
+    def recv_buffer(self) -> bytearray:
+        """payload as the receive buffer itself (no copy): for zero-copy decoders (utils/tensor_wire.py)"""
+        length = int.from_bytes(self._recv_exact(self.payload_length_size), byteorder="big")
+        return self._recv_exact(length)
 
     def recv_message(self) -> Tuple[str, bytes]:
         return self.recv_header(), self.recv_raw()

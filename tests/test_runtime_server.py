@@ -79,7 +79,8 @@ def test_expert_backend_semantics():
     (y2,) = be.forward(x)
     assert not torch.allclose(y1, y2)
     info = be.get_info()
-    assert set(info) == {"forward_schema", "outputs_schema", "keyword_names"} and info["keyword_names"] == ()
+    # the three keys of the reference + the negotiated raw-tensor-wire flag (ignored by reference clients)
+    assert set(info) == {"forward_schema", "outputs_schema", "keyword_names", "tensor_wire"} and info["keyword_names"] == ()
     ckpt = be.checkpoint()
     be2 = make_backend()
     be2.load_checkpoint(ckpt)
@@ -140,7 +141,7 @@ def test_remote_expert_forward_backward_over_tcp(server):
     assert not torch.allclose(remote(x.detach()), expected)  # the server trained on our backward
     with pytest.raises(TypeError):
         remote(x, x)
-    assert set(remote.info) == {"forward_schema", "outputs_schema", "keyword_names"}
+    assert set(remote.info) == {"forward_schema", "outputs_schema", "keyword_names", "tensor_wire"}
 
 
 def test_server_batches_concurrent_trainers_and_reports_errors(server):
@@ -175,3 +176,32 @@ def test_runtime_serves_oldest_pool_first():
     time.sleep(0.01)
     b1.forward_pool.submit_task(torch.zeros(1, 16))
     assert rt._next_pool(timeout=0) is b2.forward_pool  # older task wins (the reference would pick the newest)
+
+
+def test_tensor_wire_roundtrip_and_protocol_negotiation(server):
+    """raw-tensor frames (utils/tensor_wire.py): exact round trip; our client uses them against our server; a client that
+    speaks the reference protocol ('fwd_' + torch.save) gets the same answer from the same server"""
+    from lah_b200.utils import tensor_wire, Connection, PytorchSerializer
+    tensors = (torch.randn(3, 5), torch.arange(6).view(2, 3), torch.randn(4).to(torch.bfloat16), torch.tensor([True, False]),
+               torch.empty(0, 7), torch.randn(2, 2, 2).to(torch.float16))
+    parts, total = tensor_wire.encode("some.uid", tensors)
+    blob = b"".join(bytes(p) for p in parts)
+    assert len(blob) == total
+    uid, back = tensor_wire.decode(bytearray(blob))
+    assert uid == "some.uid" and len(back) == len(tensors)
+    for a, b in zip(tensors, back):
+        assert a.dtype == b.dtype and a.shape == b.shape and torch.equal(a, b)
+    assert not tensor_wire.supported((torch.randn(2), "not a tensor"))
+    # negotiated fast path == reference path
+    remote = lib.RemoteExpert("expert2", "127.0.0.1", server.port)
+    assert remote.info["tensor_wire"] == 1
+    x = torch.randn(9, 16, requires_grad=True)
+    y_fast = remote(x)
+    with Connection.create("127.0.0.1", server.port) as c:      # what a reference client sends
+        c.send_raw("fwd_", PytorchSerializer.dumps(("expert2", (x.detach(),))))
+        header, message = c.recv_message()
+    assert header == "rest"
+    (y_ref,) = PytorchSerializer.loads(message)
+    assert torch.allclose(y_fast, y_ref)
+    y_fast.sum().backward()                                       # 'bwdT' works too (the server steps the expert)
+    assert x.grad is not None and x.grad.shape == x.shape
