@@ -27,6 +27,18 @@ from ...models.layers import name_to_block, SEQ_LEN
 from ...ops import kernels as K, native
 
 
+def chain_schedule(tick: int, rank: int, world: int, num_layers: int):
+    """which wave this rank works on at pipeline tick ``tick`` and where that wave is in the chain.
+
+    Layer i of the chain lives on rank i % world (the reference client interleaves the servers the same way,
+    throughput_client.py:48); wave w enters layer 0 at tick w, so at tick t rank r holds wave (t - r) % world, which is at
+    chain position (t - wave) % num_layers — a layer hosted by r by construction.  Returns (wave, global layer, local layer).
+    """
+    wave = (tick - rank) % world
+    layer_global = (tick - wave) % num_layers
+    return wave, layer_global, layer_global // world
+
+
 def make_parser():
     p = ArgumentParser()
     p.add_argument("--block-type", choices=["ffn", "transformer"], default="transformer")
@@ -88,9 +100,8 @@ def run(args):
 
     def one_tick():
         t = tick[0]
-        wave = (t - rank) % world
-        layer_global = (t - wave) % L               # this wave's position in the chain; lives here: % world == rank
-        layers[layer_global // world](shape(bufs[t % 2]), out=shape(peer_bufs[(t + 1) % 2]))
+        _, _, local_layer = chain_schedule(t, rank, world, L)
+        layers[local_layer](shape(bufs[t % 2]), out=shape(peer_bufs[(t + 1) % 2]))
         if world > 1:
             K.signal_wait(flags_off, K.SLOT_DISPATCH, t + 1, status, signal=True, wait=True)
         tick[0] = t + 1

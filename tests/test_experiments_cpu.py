@@ -41,3 +41,22 @@ def test_throughput_cli_flag_parity():
             c.max_ping) == (10, 100, 10, 2048, 10, 0.2)
     i = inbox_chain.make_parser().parse_args([])
     assert (i.layers_per_gpu, i.jobs, i.block_type) == (56, 64, "transformer")
+
+
+def test_inbox_chain_schedule_invariants():
+    """pipeline schedule of the in-box throughput experiment: every rank always has exactly one wave, a wave walks the
+    chain in order, and layer i is always executed by rank i % world"""
+    from lah_b200.experiments.throughput.inbox_chain import chain_schedule
+    for world, per_gpu in ((1, 5), (2, 3), (8, 56)):
+        L = world * per_gpu
+        position = {}
+        for t in range(world, world + 2 * L):          # steady state (every wave has entered the chain)
+            waves = set()
+            for r in range(world):
+                wave, layer, local = chain_schedule(t, r, world, L)
+                assert layer % world == r and local == layer // world and 0 <= local < per_gpu
+                waves.add(wave)
+                if wave in position:
+                    assert layer == (position[wave] + 1) % L      # the wave advanced by exactly one layer
+                position[wave] = layer
+            assert waves == set(range(world))               # all waves in flight, one per rank
