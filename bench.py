@@ -254,6 +254,7 @@ def _measure_ours(args, rank, world, local_rank, B, capacity_factor):
             finally:
                 trainer.ctx.heap.close()
 
+    barrier_sync(world)   # ranks finish building their host batches at different times: start the first step together
     for i in range(args.warmup):
         step_device(i)
     check_all_ranks()
