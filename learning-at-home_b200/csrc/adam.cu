@@ -31,11 +31,23 @@ struct AdamArgs {
     // gradients that the ranks in mask shadow_of[2g+1] left in shadow slot shadow_of[2g] of their (symmetric) gradient
     // buffers (+ my own partial in the owned slot when my bit is set): the data-parallel reduce is fused into the update
     int G_active; const int* shadow_of; long long shadow_g_off; int me;
+    // optional restriction to a subset of the segments (seg_mask != 0): the kernel then walks only the concatenation of the
+    // selected segments (the fused wgrad+AMSGrad kernel of small_m.cu owns the weight matrices, this one the small vectors)
+    int num_ranges; long long r_start[6]; long long r_cum[7];
 };
 
 __global__ void __launch_bounds__(256) adam_kernel(AdamArgs a) {
     const long long stride = static_cast<long long>(gridDim.x) * blockDim.x * 4;
-    for (long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4; i < a.total; i += stride) {
+    const long long span = a.num_ranges ? a.r_cum[a.num_ranges] : a.total;
+    for (long long j = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4; j < span; j += stride) {
+        long long i = j;
+        if (a.num_ranges) {
+            int r = 0;
+#pragma unroll
+            for (int t = 1; t < 6; ++t)
+                if (t < a.num_ranges && j >= a.r_cum[t]) r = t;
+            i = a.r_start[r] + (j - a.r_cum[r]);
+        }
         int sg = 0;
 #pragma unroll
         for (int t = 1; t < 12; ++t)
@@ -133,7 +145,7 @@ int lah_adam_step(float* p, float* g, float* m, float* v, float* vmax, void* p_b
                   const int* step, const int* group_rows, int step_scalar, float lr, float beta1, float beta2, float eps,
                   float weight_decay, int amsgrad, int zero_mask, int world, long long peer_grad_off,
                   const unsigned long long* peer_bases, float grad_scale, int G_active, const int* shadow_of,
-                  long long shadow_g_off, int me, cudaStream_t st) {
+                  long long shadow_g_off, int me, int seg_mask, cudaStream_t st) {
     if (num_segs < 1 || num_segs > 12) return -2;
     AdamArgs a;
     a.num_segs = num_segs;
@@ -153,8 +165,26 @@ int lah_adam_step(float* p, float* g, float* m, float* v, float* vmax, void* p_b
     a.zero_mask = zero_mask; a.world = world; a.peer_grad_off = peer_grad_off; a.grad_scale = grad_scale;
     a.G_active = G_active > 0 ? G_active : G; a.shadow_of = shadow_of; a.shadow_g_off = shadow_g_off; a.me = me;
     for (int i = 0; i < 8; ++i) a.peer_base[i] = (peer_bases && i < world) ? (char*)peer_bases[i] : nullptr;
-    if (a.total <= 0) return 0;
-    long long blocks = (a.total / 4 + 255) / 256;
+    a.num_ranges = 0;
+    a.r_cum[0] = 0;
+    if (seg_mask) {   // adjacent selected segments merge into one range
+        for (int s = 0; s < num_segs; ++s) {
+            if (!((seg_mask >> s) & 1)) continue;
+            const long long len = seg_n[s] * G;
+            if (a.num_ranges && a.r_start[a.num_ranges - 1] + (a.r_cum[a.num_ranges] - a.r_cum[a.num_ranges - 1]) == a.seg_start[s]) {
+                a.r_cum[a.num_ranges] += len;
+            } else {
+                if (a.num_ranges == 6) return -2;
+                a.r_start[a.num_ranges] = a.seg_start[s];
+                a.r_cum[a.num_ranges + 1] = a.r_cum[a.num_ranges] + len;
+                ++a.num_ranges;
+            }
+        }
+        if (!a.num_ranges) return 0;
+    }
+    const long long span = a.num_ranges ? a.r_cum[a.num_ranges] : a.total;
+    if (span <= 0) return 0;
+    long long blocks = (span / 4 + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
     adam_kernel<<<(int)blocks, 256, 0, st>>>(a);
     return -(int)cudaGetLastError();

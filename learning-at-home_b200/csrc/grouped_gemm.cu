@@ -44,6 +44,7 @@ struct GemmParams {
     // receive-side fusion: the TMA producer waits until every source rank's dispatch flag reached `wait_epoch`
     const int* wait_flags;     // [wait_count] local flag words written by the peers (st.release.sys), or nullptr
     int wait_count, wait_epoch;
+    const int* epoch_base;   // device-side epoch base added to wait_epoch (nullptr: 0), see moe.cu Peers::step_ctr
     int* status;
 };
 
@@ -131,7 +132,7 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA, const _
         if (p.wait_flags) {  // rows pushed by peer GPUs over NVLink must have landed before the first TMA load
             const unsigned long long t_wait = globaltimer_ns();
             for (int sidx = 0; sidx < p.wait_count; ++sidx)
-                if (!spin_flag_ge(p.wait_flags + sidx, p.wait_epoch)) atomicOr(p.status, 1);
+                if (!spin_flag_ge(p.wait_flags + sidx, p.wait_epoch + (p.epoch_base ? *p.epoch_base : 0))) atomicOr(p.status, 1);
             // exposed communication wait (ns) of this rank: status[2..3] is a 64-bit counter (EngineContext.wait_ns)
             if (blockIdx.x == 0) atomicAdd(reinterpret_cast<unsigned long long*>(p.status + 2), globaltimer_ns() - t_wait);
             fence_proxy_async_global();
@@ -382,6 +383,8 @@ using namespace lah;
 // ------------------------------------------------------------------------------------------------
 // C ABI (called from python via ctypes; see ops/native.py)
 // ------------------------------------------------------------------------------------------------
+extern "C" const int* lah_get_epoch_base();
+
 extern "C" {
 
 // C[rows, N] = A[rows, K] @ B[g]^T (+bias) (+residual)
@@ -418,7 +421,7 @@ int lah_gemm_mgroup(const void* A, long long lda, int a_rows, const void* B, int
     p.N = N; p.K = K; p.M = m_valid; p.num_groups = G; p.num_m_tiles = num_m_tiles; p.tile_group = tile_group;
     p.group_off = nullptr; p.C = C; p.ldc = ldc; p.c_group_stride = 0; p.bias = bias;
     p.residual = reinterpret_cast<const bf16*>(residual); p.ldr = ldr;
-    p.wait_flags = wait_flags; p.wait_count = wait_count; p.wait_epoch = wait_epoch; p.status = status;
+    p.wait_flags = wait_flags; p.wait_count = wait_count; p.wait_epoch = wait_epoch; p.epoch_base = lah_get_epoch_base(); p.status = status;
 #define LAH_LAUNCH_M(BN, ST)                                                                                   \
     if (!b_mn && !out_f32) return launch<BN, ST, MODE_MGROUP, false, false, false>(p, tmA, tmB, max_ctas, stream); \
     if (b_mn && !out_f32) return launch<BN, ST, MODE_MGROUP, false, true, false>(p, tmA, tmB, max_ctas, stream);   \
@@ -454,7 +457,7 @@ int lah_gemm_kgroup(const void* A, long long lda, const void* B, long long ldb, 
     GemmParams p;
     p.N = N; p.K = 0; p.M = M; p.num_groups = G; p.num_m_tiles = 0; p.tile_group = nullptr; p.group_off = group_off;
     p.C = C; p.ldc = ldc; p.c_group_stride = c_group_stride; p.bias = nullptr; p.residual = nullptr; p.ldr = 0;
-    p.wait_flags = nullptr; p.wait_count = 0; p.wait_epoch = 0; p.status = nullptr;
+    p.wait_flags = nullptr; p.wait_count = 0; p.wait_epoch = 0; p.epoch_base = nullptr; p.status = nullptr;
     if (block_n == 256) return launch<256, 4, MODE_KGROUP, true, true, true>(p, tmA, tmB, max_ctas, stream);
     if (block_n == 128) return launch<128, 6, MODE_KGROUP, true, true, true>(p, tmA, tmB, max_ctas, stream);
     if (block_n == 64) return launch<64, 8, MODE_KGROUP, true, true, true>(p, tmA, tmB, max_ctas, stream);

@@ -48,8 +48,10 @@ struct Params {
     long long ldr;
     const int* wait_flags;   // receive-side fusion (see grouped_gemm.cu)
     int wait_count, wait_epoch;
+    const int* epoch_base;   // device-side epoch base added to wait_epoch (nullptr: 0), see moe.cu Peers::step_ctr
     int* status;
     int act;                 // epilogue activation after the bias: 0 none, 1 ReLU, 2 GELU (erf)
+    int accumulate;          // KGROUP (fp32 out): C += result (gradient accumulation across steps, update_every_*)
 };
 
 template <int MODE, bool A_MN, bool B_MN, bool OUT_F32>
@@ -133,7 +135,7 @@ gemm2_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const __gr
         if (p.wait_flags) {  // rows pushed by peer GPUs over NVLink must have landed before the first TMA load
             const unsigned long long t_wait = globaltimer_ns();
             for (int sidx = 0; sidx < p.wait_count; ++sidx)
-                if (!spin_flag_ge(p.wait_flags + sidx, p.wait_epoch)) atomicOr(p.status, 1);
+                if (!spin_flag_ge(p.wait_flags + sidx, p.wait_epoch + (p.epoch_base ? *p.epoch_base : 0))) atomicOr(p.status, 1);
             // exposed communication wait (ns) of this rank: status[2..3] is a 64-bit counter (EngineContext.wait_ns)
             if (blockIdx.x == 0) atomicAdd(reinterpret_cast<unsigned long long*>(p.status + 2), globaltimer_ns() - t_wait);
             fence_proxy_async_global();
@@ -310,7 +312,13 @@ gemm2_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const __gr
                 for (int i = 0; i < 32 / ROWS_PER_INSTR; ++i) {
                     const int rl = i * ROWS_PER_INSTR + lane / LANES_PER_ROW;
                     const int grow = row_base + rl;
-                    const int4 q = *reinterpret_cast<const int4*>(slab + rl * EPI_ROW_BYTES + piece * 16);
+                    int4 q = *reinterpret_cast<const int4*>(slab + rl * EPI_ROW_BYTES + piece * 16);
+                    if (MODE == MODE_KGROUP && OUT_F32 && p.accumulate) {
+                        const float4 o = *reinterpret_cast<const float4*>(cbase + static_cast<long long>(grow) * row_bytes);
+                        float4 n = *reinterpret_cast<float4*>(&q);
+                        n.x += o.x; n.y += o.y; n.z += o.z; n.w += o.w;
+                        q = *reinterpret_cast<int4*>(&n);
+                    }
                     if (MODE == MODE_KGROUP || grow < p.M)
                         *reinterpret_cast<int4*>(cbase + static_cast<long long>(grow) * row_bytes) = q;
                 }
@@ -400,6 +408,8 @@ static int launch2(const Params& p, const CUtensorMap& tmA, const CUtensorMap& t
 using namespace lah;
 using namespace lah::pair;
 
+extern "C" const int* lah_get_epoch_base();
+
 extern "C" {
 
 // same contract as lah_gemm_mgroup, but expert groups must be padded to 256 rows; tile_group still has one entry per
@@ -434,7 +444,7 @@ int lah_gemm_mgroup2(const void* A, long long lda, int a_rows, const void* B, in
     p.N = N; p.K = K; p.M = m_valid; p.num_groups = G; p.num_m_tiles = (num_m_tiles128 + 1) / 2; p.tile_group = tile_group;
     p.group_off = nullptr; p.C = C; p.ldc = ldc; p.c_group_stride = 0; p.bias = bias;
     p.residual = reinterpret_cast<const bf16*>(residual); p.ldr = ldr;
-    p.wait_flags = wait_flags; p.wait_count = wait_count; p.wait_epoch = wait_epoch; p.status = status; p.act = act;
+    p.wait_flags = wait_flags; p.wait_count = wait_count; p.wait_epoch = wait_epoch; p.epoch_base = lah_get_epoch_base(); p.status = status; p.act = act; p.accumulate = 0;
     if (!b_mn && !out_f32) return launch2<MODE_MGROUP, false, false, false>(p, tmA, tmB, max_ctas, stream);
     if (b_mn && !out_f32) return launch2<MODE_MGROUP, false, true, false>(p, tmA, tmB, max_ctas, stream);
     if (!b_mn && out_f32) return launch2<MODE_MGROUP, false, false, true>(p, tmA, tmB, max_ctas, stream);
@@ -443,7 +453,7 @@ int lah_gemm_mgroup2(const void* A, long long lda, int a_rows, const void* B, in
 
 int lah_gemm_kgroup2(const void* A, long long lda, const void* B, long long ldb, int total_rows, int G, int M, int N,
                      const int* group_off, float* C, long long ldc, long long c_group_stride, int max_ctas,
-                     cudaStream_t stream) {
+                     int accumulate, cudaStream_t stream) {
     if ((M % 256) || (N % 32) || (lda % 8) || (ldb % 8)) return -2;
     CUtensorMap tmA, tmB;
     {
@@ -463,7 +473,7 @@ int lah_gemm_kgroup2(const void* A, long long lda, const void* B, long long ldb,
     Params p;
     p.N = N; p.K = 0; p.M = M; p.num_groups = G; p.num_m_tiles = 0; p.tile_group = nullptr; p.group_off = group_off;
     p.C = C; p.ldc = ldc; p.c_group_stride = c_group_stride; p.bias = nullptr; p.residual = nullptr; p.ldr = 0;
-    p.wait_flags = nullptr; p.wait_count = 0; p.wait_epoch = 0; p.status = nullptr; p.act = 0;
+    p.wait_flags = nullptr; p.wait_count = 0; p.wait_epoch = 0; p.epoch_base = nullptr; p.status = nullptr; p.act = 0; p.accumulate = accumulate;
     return launch2<MODE_KGROUP, true, true, true>(p, tmA, tmB, max_ctas, stream);
 }
 

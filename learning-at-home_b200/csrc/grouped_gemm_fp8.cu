@@ -55,6 +55,7 @@ struct Params {
     long long ldr;
     const int* wait_flags;
     int wait_count, wait_epoch;
+    const int* epoch_base;   // device-side epoch base added to wait_epoch (nullptr: 0), see moe.cu Peers::step_ctr
     int* status;
     int act;
 };
@@ -153,7 +154,7 @@ gemm_fp8_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const _
         if (p.wait_flags) {
             const unsigned long long t_wait = globaltimer_ns();
             for (int sidx = 0; sidx < p.wait_count; ++sidx)
-                if (!spin_flag_ge(p.wait_flags + sidx, p.wait_epoch)) atomicOr(p.status, 1);
+                if (!spin_flag_ge(p.wait_flags + sidx, p.wait_epoch + (p.epoch_base ? *p.epoch_base : 0))) atomicOr(p.status, 1);
             // exposed communication wait (ns) of this rank: status[2..3] is a 64-bit counter (EngineContext.wait_ns)
             if (blockIdx.x == 0) atomicAdd(reinterpret_cast<unsigned long long*>(p.status + 2), globaltimer_ns() - t_wait);
             fence_proxy_async_global();
@@ -482,6 +483,8 @@ static int launch_fp8(const Params& p, const CUtensorMap& tmA, const CUtensorMap
 using namespace lah;
 using namespace lah::f8;
 
+extern "C" const int* lah_get_epoch_base();
+
 extern "C" {
 
 // bytes of the scale-factor buffer for `rows` rows per group (tile_rows = 128: activations, 192: weights)
@@ -555,7 +558,7 @@ int lah_gemm_mgroup_fp8(const void* A, long long lda, int a_rows, const void* sf
     p.N = N; p.K = K; p.M = m_valid; p.num_groups = G; p.num_m_tiles = (num_m_tiles128 + 1) / 2; p.n_tiles = n_tiles;
     p.num_kb = num_kb; p.tile_group = tile_group; p.C = C; p.ldc = ldc; p.bias = bias;
     p.residual = reinterpret_cast<const bf16*>(residual); p.ldr = ldr;
-    p.wait_flags = wait_flags; p.wait_count = wait_count; p.wait_epoch = wait_epoch; p.status = status; p.act = act;
+    p.wait_flags = wait_flags; p.wait_count = wait_count; p.wait_epoch = wait_epoch; p.epoch_base = lah_get_epoch_base(); p.status = status; p.act = act;
     return out_f32 ? launch_fp8<true>(p, tmA, tmB, tmSFA, tmSFB, max_ctas, stream)
                    : launch_fp8<false>(p, tmA, tmB, tmSFA, tmSFB, max_ctas, stream);
 }

@@ -42,12 +42,12 @@ template <int C, bool QUANT, int R>
 __global__ void __launch_bounds__(256, 2) ln_relu_fwd_kernel(
     const bf16* __restrict__ h, bf16* __restrict__ a, float* __restrict__ mean_out, float* __restrict__ rstd_out,
     const float* __restrict__ gamma, const float* __restrict__ beta, const int* __restrict__ tile_group, int rows,
-    int relu, uint8_t* __restrict__ aq, uint8_t* __restrict__ sf) {
+    int relu, uint8_t* __restrict__ aq, uint8_t* __restrict__ sf, int tile_shift) {
     constexpr int NV = C / 256;  // int4 (8 x bf16) chunks per lane
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row0 = (blockIdx.x * 8 + warp) * R;
     if (row0 >= rows) return;
-    const int g = tile_group ? __ldg(tile_group + (row0 >> 7)) : 0;
+    const int g = tile_group ? __ldg(tile_group + (row0 >> tile_shift)) : 0;
     if (g < 0) return;
     // rows stay PACKED (bf16x2) in registers: 4 regs per 8 values; values are unpacked on the fly in each pass
     int4 q[R][NV];
@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(C / 8, (C <= 2048) ? 2 : 1) ln_relu_bwd_kernel
                                                             const float* __restrict__ beta, bf16* __restrict__ dh,
                                                             float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                             float* __restrict__ dbias,
-                                                            const int* __restrict__ tile_group, int rows, int relu) {
+                                                            const int* __restrict__ tile_group, int rows, int relu, int tile_rows) {
     constexpr int THREADS = C / 8;
     constexpr int WARPS = THREADS / 32;
     constexpr int RB = (C >= 4096) ? 2 : 4;  // rows per batch (register blocking)
@@ -192,8 +192,8 @@ __global__ void __launch_bounds__(C / 8, (C <= 2048) ? 2 : 1) ln_relu_bwd_kernel
 #pragma unroll
     for (int t = 0; t < 8; ++t) acc_dg[t] = acc_db[t] = acc_dbias[t] = 0.f;
 
-    const int row0 = tile * 128;
-    const int row_end = min(rows, row0 + 128);
+    const int row0 = tile * tile_rows;
+    const int row_end = min(rows, row0 + tile_rows);
     // software pipeline: the loads of batch i+1 are in flight while batch i is reduced / written
     int4 nqa[RB], nqh[RB];
     float nmu[RB], nrs[RB];
@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(C / 8, (C <= 2048) ? 2 : 1) ln_relu_bwd_kernel
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(512) grouped_colsum_kernel(const bf16* __restrict__ x, long long ldx,
                                                              float* __restrict__ out, int C,
-                                                             const int* __restrict__ tile_group, int rows) {
+                                                             const int* __restrict__ tile_group, int rows, int tile_rows) {
     __shared__ float2 sm[4][128];
     const int tile = blockIdx.x;
     const int g = tile_group ? __ldg(tile_group + tile) : 0;
@@ -319,7 +319,7 @@ __global__ void __launch_bounds__(512) grouped_colsum_kernel(const bf16* __restr
     const int phase = threadIdx.x >> 7;       // 0..3
     const int col = blockIdx.y * 256 + cp * 2;
     if (col >= C) return;                      // C is a multiple of 256 in practice; whole warps exit together
-    const int row0 = tile * 128, row_end = min(rows, row0 + 128);
+    const int row0 = tile * tile_rows, row_end = min(rows, row0 + tile_rows);
     float2 acc = make_float2(0.f, 0.f);
     for (int r = row0 + phase; r < row_end; r += 4) {
         const uint32_t u = __ldg(reinterpret_cast<const uint32_t*>(x + static_cast<long long>(r) * ldx + col));
@@ -347,23 +347,37 @@ using namespace lah;
 
 extern "C" {
 
-int lah_ln_relu_fwd(const void* h, void* a, float* mean, float* rstd, const float* gamma, const float* beta,
-                    const int* tile_group, int rows, int C, int relu, cudaStream_t st) {
+static int shift_of(int tile_rows) {
+    int s = 0;
+    while ((1 << s) < tile_rows) ++s;
+    return ((1 << s) == tile_rows && tile_rows >= 8) ? s : -1;
+}
+
+// tile_rows: rows per tile_group entry (power of two >= 8; 128 for the padded big-batch layout, 16 for the small-M layout)
+int lah_ln_relu_fwd_t(const void* h, void* a, float* mean, float* rstd, const float* gamma, const float* beta,
+                      const int* tile_group, int rows, int C, int relu, int tile_rows, cudaStream_t st) {
     if (rows <= 0) return 0;
+    const int tile_shift = shift_of(tile_rows);
+    if (tile_shift < 0) return -2;
 #define LAH_LN_FWD(CC)                                                                                          \
     if (C == CC) {                                                                                              \
         constexpr int RR = LnFwdCfg<CC>::R;                                                                     \
         if (ln_rows_per_warp(RR) == 1)                                                                          \
             ln_relu_fwd_kernel<CC, false, 1><<<(rows + 7) / 8, 256, 0, st>>>(                                  \
-                (const bf16*)h, (bf16*)a, mean, rstd, gamma, beta, tile_group, rows, relu, nullptr, nullptr);   \
+                (const bf16*)h, (bf16*)a, mean, rstd, gamma, beta, tile_group, rows, relu, nullptr, nullptr, tile_shift);   \
         else                                                                                                    \
             ln_relu_fwd_kernel<CC, false, RR><<<(rows + 8 * RR - 1) / (8 * RR), 256, 0, st>>>(                 \
-                (const bf16*)h, (bf16*)a, mean, rstd, gamma, beta, tile_group, rows, relu, nullptr, nullptr);   \
+                (const bf16*)h, (bf16*)a, mean, rstd, gamma, beta, tile_group, rows, relu, nullptr, nullptr, tile_shift);   \
         return -(int)cudaGetLastError();                                                                        \
     }
     LAH_LN_FWD(256) LAH_LN_FWD(512) LAH_LN_FWD(1024) LAH_LN_FWD(2048) LAH_LN_FWD(4096)
 #undef LAH_LN_FWD
     return -2;
+}
+
+int lah_ln_relu_fwd(const void* h, void* a, float* mean, float* rstd, const float* gamma, const float* beta,
+                    const int* tile_group, int rows, int C, int relu, cudaStream_t st) {
+    return lah_ln_relu_fwd_t(h, a, mean, rstd, gamma, beta, tile_group, rows, C, relu, 128, st);
 }
 
 // same + MXFP8 copy of the output (aq: e4m3 [rows, C]; sf: activation scale layout, tile_rows = 128); a may be NULL
@@ -375,10 +389,10 @@ int lah_ln_relu_fwd_q(const void* h, void* a, float* mean, float* rstd, const fl
         constexpr int RR = LnFwdCfg<CC>::R;                                                                     \
         if (ln_rows_per_warp(RR) == 1)                                                                          \
             ln_relu_fwd_kernel<CC, true, 1><<<(rows + 7) / 8, 256, 0, st>>>(                                  \
-                (const bf16*)h, (bf16*)a, mean, rstd, gamma, beta, tile_group, rows, relu, (uint8_t*)aq, (uint8_t*)sf);   \
+                (const bf16*)h, (bf16*)a, mean, rstd, gamma, beta, tile_group, rows, relu, (uint8_t*)aq, (uint8_t*)sf, 7);   \
         else                                                                                                    \
             ln_relu_fwd_kernel<CC, true, RR><<<(rows + 8 * RR - 1) / (8 * RR), 256, 0, st>>>(                 \
-                (const bf16*)h, (bf16*)a, mean, rstd, gamma, beta, tile_group, rows, relu, (uint8_t*)aq, (uint8_t*)sf);   \
+                (const bf16*)h, (bf16*)a, mean, rstd, gamma, beta, tile_group, rows, relu, (uint8_t*)aq, (uint8_t*)sf, 7);   \
         return -(int)cudaGetLastError();                                                                        \
     }
     LAH_LN_FWD(256) LAH_LN_FWD(512) LAH_LN_FWD(1024) LAH_LN_FWD(2048) LAH_LN_FWD(4096)
@@ -386,16 +400,17 @@ int lah_ln_relu_fwd_q(const void* h, void* a, float* mean, float* rstd, const fl
     return -2;
 }
 
-int lah_ln_relu_bwd(const void* da, const void* h, const float* mean, const float* rstd, const float* gamma,
-                    const float* beta, void* dh, float* dgamma, float* dbeta, float* dbias, const int* tile_group,
-                    int rows, int C, int relu, cudaStream_t st) {
+int lah_ln_relu_bwd_t(const void* da, const void* h, const float* mean, const float* rstd, const float* gamma,
+                      const float* beta, void* dh, float* dgamma, float* dbeta, float* dbias, const int* tile_group,
+                      int rows, int C, int relu, int tile_rows, cudaStream_t st) {
     if (rows <= 0) return 0;
-    const int grid = (rows + 127) / 128;
+    if (shift_of(tile_rows) < 0) return -2;
+    const int grid = (rows + tile_rows - 1) / tile_rows;
 #define LAH_LN_BWD(CC)                                                                                          \
     if (C == CC) {                                                                                              \
         ln_relu_bwd_kernel<CC><<<grid, CC / 8, 0, st>>>((const bf16*)da, (const bf16*)h, mean, rstd, gamma,    \
                                                         beta, (bf16*)dh, dgamma, dbeta, dbias, tile_group,     \
-                                                        rows, relu);                                            \
+                                                        rows, relu, tile_rows);                                 \
         return -(int)cudaGetLastError();                                                                        \
     }
     LAH_LN_BWD(256) LAH_LN_BWD(512) LAH_LN_BWD(1024) LAH_LN_BWD(2048) LAH_LN_BWD(4096)
@@ -403,13 +418,24 @@ int lah_ln_relu_bwd(const void* da, const void* h, const float* mean, const floa
     return -2;
 }
 
+int lah_ln_relu_bwd(const void* da, const void* h, const float* mean, const float* rstd, const float* gamma,
+                    const float* beta, void* dh, float* dgamma, float* dbeta, float* dbias, const int* tile_group,
+                    int rows, int C, int relu, cudaStream_t st) {
+    return lah_ln_relu_bwd_t(da, h, mean, rstd, gamma, beta, dh, dgamma, dbeta, dbias, tile_group, rows, C, relu, 128, st);
+}
+
+int lah_grouped_colsum_t(const void* x, long long ldx, float* out, int C, const int* tile_group, int rows, int tile_rows,
+                         cudaStream_t st) {
+    if (rows <= 0) return 0;
+    if (C % 256 || shift_of(tile_rows) < 0) return -2;
+    dim3 grid((rows + tile_rows - 1) / tile_rows, (C + 255) / 256);
+    grouped_colsum_kernel<<<grid, 512, 0, st>>>((const bf16*)x, ldx, out, C, tile_group, rows, tile_rows);
+    return -(int)cudaGetLastError();
+}
+
 int lah_grouped_colsum(const void* x, long long ldx, float* out, int C, const int* tile_group, int rows,
                        cudaStream_t st) {
-    if (rows <= 0) return 0;
-    if (C % 256) return -2;
-    dim3 grid((rows + 127) / 128, (C + 255) / 256);
-    grouped_colsum_kernel<<<grid, 512, 0, st>>>((const bf16*)x, ldx, out, C, tile_group, rows);
-    return -(int)cudaGetLastError();
+    return lah_grouped_colsum_t(x, ldx, out, C, tile_group, rows, 128, st);
 }
 
 }  // extern "C"

@@ -31,7 +31,16 @@ struct Peers {
     int world;
     int me;
     unsigned long long* wait_ns;  // optional device counter: ns this rank spent blocked on peer flags ("exposed" comm)
+    // device-resident step counters (CUDA-graph replay: nothing that changes from step to step is a kernel argument):
+    //   step_ctr[0] = epoch base added to every (step-relative) epoch argument;  step_ctr[2..3] = 64-bit token base added to
+    //   the gate's token_offset (failure-injection RNG stream).  Bumped by step_begin_kernel.  nullptr -> 0.
+    int* step_ctr;
+    int spin_timeout_ms;          // flag-wait timeout (0 -> ~10 s); a timed-out wait raises STATUS_TIMEOUT and goes on
 };
+
+__device__ __forceinline__ int epoch_of(const Peers& peers, int rel) {
+    return rel + (peers.step_ctr ? *reinterpret_cast<volatile const int*>(peers.step_ctr) : 0);
+}
 
 struct GridSpec {
     int ndim;
@@ -52,10 +61,11 @@ __device__ __forceinline__ float hash_uniform(unsigned long long x) {
     return static_cast<float>(x >> 40) * (1.0f / 16777216.0f);
 }
 
-__device__ __forceinline__ bool spin_until_ge(const int* flag, int epoch, int* status) {
+__device__ __forceinline__ bool spin_until_ge(const int* flag, int epoch, int* status, int timeout_ms = 0) {
     const long long t0 = clock64();
+    const long long limit = timeout_ms > 0 ? static_cast<long long>(timeout_ms) * 2000000ll : SPIN_TIMEOUT_CYCLES;
     while (ld_acquire_sys(flag) < epoch) {
-        if (clock64() - t0 > SPIN_TIMEOUT_CYCLES) {
+        if (clock64() - t0 > limit) {
             atomicOr(status, STATUS_TIMEOUT);
             return false;
         }
@@ -78,7 +88,9 @@ __global__ void __launch_bounds__(256) gate_topk_kernel(const float* __restrict_
                                                         const unsigned char* __restrict__ alive, float failure_rate,
                                                         unsigned long long seed, long long token_offset,
                                                         int* __restrict__ idx_out, float* __restrict__ w_out,
-                                                        int* __restrict__ pos_out, int* __restrict__ counts) {
+                                                        int* __restrict__ pos_out, int* __restrict__ counts,
+                                                        const int* __restrict__ step_ctr) {
+    if (step_ctr) token_offset += *reinterpret_cast<const long long*>(step_ctr + 2);
     extern __shared__ float s_logits[];  // [8 warps][gs.total]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.x * 8 + warp;
@@ -201,8 +213,9 @@ struct LayoutArgs {
     int epoch;
     int E, E_loc;
     int max_rows;            // capacity of the receive buffers (rows)
-    int max_tiles;           // max_rows / 128
-    int align;               // group padding in rows: 128 (1-CTA GEMM) or 256 (CTA-pair GEMM)
+    int max_tiles;           // max_rows / tile_rows
+    int align;               // group padding in rows: 128 (1-CTA GEMM), 256 (CTA-pair GEMM) or 16 (small-M swap-AB path)
+    int tile_rows;           // rows per tile_group entry: min(align, 128)
     int* counts;             // [E] local counts (zeroed on exit)
     int* dst_row;            // [E]  row (in route_owner[e]'s buffer) where MY first row for expert e goes
     int* group_off;          // [E_loc + S_max + 1] padded offsets of my groups (owned experts, then shadow slots)
@@ -240,6 +253,7 @@ __global__ void __launch_bounds__(1024) layout_exchange_kernel(Peers peers, Layo
     __shared__ int s_red_v[32], s_red_i[32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int me = peers.me, world = peers.world;
+    a.epoch = epoch_of(peers, a.epoch);
     // 1. publish my counts to every peer (plain P2P stores), then release the epoch flag on every peer
     for (int r = 0; r < world; ++r) {
         int* dst = reinterpret_cast<int*>(peers.base[r] + a.cnt_all_off) + static_cast<long long>(me) * a.E;
@@ -253,7 +267,7 @@ __global__ void __launch_bounds__(1024) layout_exchange_kernel(Peers peers, Layo
         // 2. wait for everybody's counts
         const int* fw = reinterpret_cast<const int*>(peers.base[me] + a.flags_off) + a.slot * MAX_WORLD + tid;
         const unsigned long long t0 = globaltimer_ns();
-        spin_until_ge(fw, a.epoch, a.status);
+        spin_until_ge(fw, a.epoch, a.status, peers.spin_timeout_ms);
         account_wait(peers, t0, world);
     }
     for (int t = tid; t < a.max_tiles; t += blockDim.x) a.tile_group[t] = -1;
@@ -390,7 +404,7 @@ __global__ void __launch_bounds__(1024) layout_exchange_kernel(Peers peers, Layo
             const int padded = (rows + a.align - 1) / a.align * a.align;
             a.group_off[G_own + s] = cur;
             a.group_rows[G_own + s] = rows;
-            for (int t = cur / 128; t < (cur + padded) / 128 && t < a.max_tiles; ++t) a.tile_group[t] = G_own + s;
+            for (int t = cur / a.tile_rows; t < (cur + padded) / a.tile_rows && t < a.max_tiles; ++t) a.tile_group[t] = G_own + s;
             int mask = 0;
             if (e >= 0)
                 for (int r = 0; r < world; ++r) mask |= (cnt_all[static_cast<long long>(r) * a.E + e] > 0) << r;
@@ -424,7 +438,7 @@ __global__ void __launch_bounds__(1024) layout_exchange_kernel(Peers peers, Layo
             const int le = e - me * a.E_loc;
             a.group_off[le] = rel;
             const int padded = (a.group_rows[le] + a.align - 1) / a.align * a.align;
-            for (int t = rel / 128; t < (rel + padded) / 128 && t < a.max_tiles; ++t) a.tile_group[t] = le;
+            for (int t = rel / a.tile_rows; t < (rel + padded) / a.tile_rows && t < a.max_tiles; ++t) a.tile_group[t] = le;
             if (a.step_rows) a.step_rows[le] = s_tot[e];
             if (a.owned_shadow) {
                 int mask = 0;
@@ -539,9 +553,10 @@ __global__ void __launch_bounds__(256) scatter_rows_kernel(Peers peers, ScatterA
         if (prev == static_cast<int>(gridDim.x) - 1) {
             *a.done_counter = 0;
             __threadfence_system();
+            const int epoch = epoch_of(peers, a.epoch);
             for (int r = 0; r < peers.world; ++r) {
                 int* f = reinterpret_cast<int*>(peers.base[r] + a.flags_off) + a.slot * MAX_WORLD + peers.me;
-                st_release_sys(f, a.epoch);
+                st_release_sys(f, epoch);
             }
         }
     }
@@ -553,6 +568,7 @@ __global__ void __launch_bounds__(256) scatter_rows_kernel(Peers peers, ScatterA
 __global__ void signal_wait_kernel(Peers peers, long long flags_off, int slot, int epoch, int do_signal, int do_wait,
                                    int* status) {
     const int lane = threadIdx.x;
+    epoch = epoch_of(peers, epoch);
     if (do_signal && lane < peers.world) {
         __threadfence_system();
         int* f = reinterpret_cast<int*>(peers.base[lane] + flags_off) + slot * MAX_WORLD + peers.me;
@@ -561,9 +577,15 @@ __global__ void signal_wait_kernel(Peers peers, long long flags_off, int slot, i
     if (do_wait && lane < peers.world) {
         const int* f = reinterpret_cast<const int*>(peers.base[peers.me] + flags_off) + slot * MAX_WORLD + lane;
         const unsigned long long t0 = globaltimer_ns();
-        spin_until_ge(f, epoch, status);
+        spin_until_ge(f, epoch, status, peers.spin_timeout_ms);
         account_wait(peers, t0, peers.world);
     }
+}
+
+// one thread: advance the device-side step counters (see Peers::step_ctr)
+__global__ void step_begin_kernel(int* step_ctr, int epoch_delta, long long token_delta) {
+    step_ctr[0] += epoch_delta;
+    *reinterpret_cast<long long*>(step_ctr + 2) += token_delta;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -586,6 +608,7 @@ struct CombineArgs {
 template <int VEC_PER_LANE>
 __global__ void __launch_bounds__(256) combine_rows_kernel(Peers peers, CombineArgs a) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (a.do_signal || a.do_wait) a.epoch = epoch_of(peers, a.epoch);
     if (a.do_signal && blockIdx.x == 0 && threadIdx.x < peers.world) {
         // everything launched before this kernel on the stream (the last expert GEMM) is complete: tell the peers
         __threadfence_system();
@@ -596,7 +619,7 @@ __global__ void __launch_bounds__(256) combine_rows_kernel(Peers peers, CombineA
         if (threadIdx.x < peers.world) {
             const int* f = reinterpret_cast<const int*>(peers.base[peers.me] + a.flags_off) + a.slot * MAX_WORLD + threadIdx.x;
             const unsigned long long t0 = globaltimer_ns();
-            spin_until_ge(f, a.epoch, a.status);
+            spin_until_ge(f, a.epoch, a.status, peers.spin_timeout_ms);
             if (blockIdx.x == 0) account_wait(peers, t0, peers.world);
         }
         __syncthreads();
@@ -790,8 +813,29 @@ int lah_set_peers(const unsigned long long* bases, int world, int me) {
     g_peers.world = world;
     g_peers.me = me;
     g_peers.wait_ns = nullptr;
+    g_peers.step_ctr = nullptr;
+    g_peers.spin_timeout_ms = 0;
     g_peers_set = true;
     return 0;
+}
+
+// device-side step counters: int32[4] (see Peers::step_ctr); NULL disables (epochs / token offsets are then absolute)
+int lah_set_step_counters(int* step_ctr) {
+    g_peers.step_ctr = step_ctr;
+    return 0;
+}
+const int* lah_get_epoch_base() { return g_peers.step_ctr; }
+
+// timeout of every peer-flag wait in ms of SM clock at ~2 GHz (0 = default ~10 s)
+int lah_set_spin_timeout_ms(int ms) {
+    g_peers.spin_timeout_ms = ms;
+    return 0;
+}
+
+int lah_step_begin(int epoch_delta, long long token_delta, cudaStream_t st) {
+    if (!g_peers.step_ctr) return -10;
+    step_begin_kernel<<<1, 1, 0, st>>>(g_peers.step_ctr, epoch_delta, token_delta);
+    return -(int)cudaGetLastError();
 }
 
 // device counter (8 bytes) that accumulates the ns this rank spends blocked on peer flags; NULL disables
@@ -824,19 +868,21 @@ int lah_gate_topk(const float* logits, int B, const int* grid, int ndim, int k, 
     if (k < 1 || k > MAX_K) return -3;
     if (B <= 0) return 0;
     gate_topk_kernel<<<(B + 7) / 8, 256, 8 * gs.total * sizeof(float), st>>>(logits, B, gs, k, alive, failure_rate, seed,
-                                                                           token_offset, idx, w, pos, counts);
+                                                                           token_offset, idx, w, pos, counts,
+                                                                           g_peers.step_ctr);
     return -(int)cudaGetLastError();
 }
 
 int lah_layout_exchange(long long cnt_all_off, long long flags_off, int slot, int epoch, int E, int E_loc, int max_rows,
-                        int align, int* counts, int* dst_row, int* group_off, int* group_rows, int* tile_group, int* total_rows,
+                        int align, int tile_rows, int* counts, int* dst_row, int* group_off, int* group_rows, int* tile_group, int* total_rows,
                         int* status, int S_max, float shadow_tol, int min_shadow_rows, int* route_owner, int* step_rows,
                         int* shadow_info, int* owned_shadow, cudaStream_t st) {
     if (!g_peers_set) return -10;
     if (E > LAYOUT_MAX_E || S_max < 0 || S_max > 2 * MAX_WORLD) return -2;
     LayoutArgs a;
     a.cnt_all_off = cnt_all_off; a.flags_off = flags_off; a.slot = slot; a.epoch = epoch; a.E = E; a.E_loc = E_loc;
-    a.max_rows = max_rows; a.max_tiles = max_rows / 128; a.align = align; a.counts = counts; a.dst_row = dst_row; a.group_off = group_off;
+    if (tile_rows <= 0 || align % tile_rows) return -2;
+    a.max_rows = max_rows; a.tile_rows = tile_rows; a.max_tiles = max_rows / tile_rows; a.align = align; a.counts = counts; a.dst_row = dst_row; a.group_off = group_off;
     a.group_rows = group_rows; a.tile_group = tile_group; a.total_rows = total_rows; a.status = status;
     a.S_max = S_max; a.shadow_tol = shadow_tol; a.min_shadow_rows = min_shadow_rows; a.route_owner = route_owner;
     a.step_rows = step_rows; a.shadow_info = shadow_info; a.owned_shadow = owned_shadow;

@@ -1,0 +1,673 @@
+// small_m.cu — the "many small requests" regime of the reference (64 trainers x batch 4 -> O(1..64) rows per expert and
+// step; /root/reference/experiments/convergence notebooks, lib/runtime/task_pool.py:105-125) on sm_100a.
+//
+// With a handful of rows per expert every expert GEMM is a WEIGHT-STREAMING problem (12.6 MB of bf16 weights per
+// active expert and forward at hid 512) and the optimizer is a STATE-STREAMING problem (fp32 p, m, v, vmax).  Two
+// kernels, both persistent / warp-specialised / TMA-fed with accumulators in TMEM:
+//
+//   swapab_kernel      D^T[out_features, tokens] = W[out_features, K] * X^T[K, tokens]   ("swap-AB": the weights sit on
+//                      the 128-wide MMA-M side, the expert's 16..128 tokens on the MMA-N side, so a group of 16 rows
+//                      costs one N=16 instruction instead of a 256-row padded tile).  Each CTA streams a 128-row slice
+//                      of one expert's weight matrix through a 6-stage TMA ring exactly once.  A_MN selects dgrad
+//                      (W^T read straight from the same [out, in] tensor as an MN-major operand).
+//   wgrad_adam_kernel  dW tile = dY^T X on tcgen05 (both operands MN-major, reduction over the expert's tokens = the
+//                      gradient reduction over all trainers that routed to it) with the per-expert AMSGrad step FUSED
+//                      INTO THE EPILOGUE: p / m / v / vmax tiles arrive through TMA (128B-swizzled smem, per-warp
+//                      3-slot ring), are updated in place from the TMEM accumulator and leave through TMA stores; the
+//                      bf16 mirror is written from registers.  The weight gradient never exists in HBM: 34 B / parameter
+//                      instead of 46 (wgrad write 4 + Adam 38 + re-read 4).
+//                      Reference semantics: one torch.optim.Adam(amsgrad=True) step per expert right after its backward
+//                      (/root/reference/lib/runtime/expert_backend.py:90-97).
+#include "sm100.cuh"
+
+namespace lah {
+namespace smallm {
+
+constexpr int BM = 128;      // MMA M: weight rows (swapab) / dY features (wgrad)
+constexpr int BK = 64;       // k elements per stage row (128 B of bf16 = one swizzle row)
+constexpr int UMMA_K = 16;
+constexpr int BN_MAX = 128;  // max tokens per MMA (swapab) / X features per tile (wgrad)
+constexpr int NUM_THREADS = 192;
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled encode_fn() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess || !ptr)
+            return nullptr;
+        fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+    }
+    return fn;
+}
+
+static int make_tmap(CUtensorMap* tm, CUtensorMapDataType dt, int esize, const void* ptr, int rank, const uint64_t* dims,
+                     const uint64_t* strides_bytes, const uint32_t* box) {
+    PFN_encodeTiled fn = encode_fn();
+    if (!fn) return -100;
+    cuuint64_t gdims[3];
+    cuuint64_t gstr[2];
+    cuuint32_t gbox[3];
+    cuuint32_t estr[3] = {1, 1, 1};
+    for (int i = 0; i < rank; ++i) {
+        gdims[i] = dims[i];
+        gbox[i] = box[i];
+    }
+    for (int i = 0; i < rank - 1; ++i) gstr[i] = strides_bytes[i];
+    (void)esize;
+    CUresult r = fn(tm, dt, rank, const_cast<void*>(ptr), gdims, gstr, gbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : -static_cast<int>(r) - 1000;
+}
+
+static int num_sms() {
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    return sms;
+}
+
+// =====================================================================================================================
+// swap-AB grouped linear
+// =====================================================================================================================
+namespace sab {
+
+constexpr int STAGES = 6;
+constexpr int A_BYTES = BM * BK * 2;          // 16 KB
+constexpr int B_BYTES = BN_MAX * BK * 2;      // 16 KB (only box_rows * 128 B are filled)
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+constexpr int SMEM_TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 1024;
+
+struct Params {
+    int G, M_out, K;          // groups, output features (rows of the weight operand), reduction length
+    const int* group_off;     // [G] first row of the group inside the token-major buffers
+    const int* group_rows;    // [G] valid rows (0: skip the group)
+    bf16* out;                // [rows, M_out]  token-major
+    long long ldo;
+    const float* bias;        // [G, M_out] or nullptr
+    const bf16* residual;     // [rows, ldr] or nullptr
+    long long ldr;
+    const int* wait_flags;    // receive-side fusion: rows pushed by the peers must have landed (see grouped_gemm.cu)
+    int wait_count, wait_epoch;
+    const int* epoch_base;    // optional device-side epoch base added to wait_epoch (CUDA-graph replay)
+    int* status;
+};
+
+__device__ __forceinline__ int box_rows_of(int nn) { return nn <= 16 ? 16 : (nn <= 32 ? 32 : (nn <= 64 ? 64 : 128)); }
+
+template <bool A_MN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+swapab_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB16,
+              const __grid_constant__ CUtensorMap tmB32, const __grid_constant__ CUtensorMap tmB64,
+              const __grid_constant__ CUtensorMap tmB128) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + BAR_OFFSET);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tmem_full = empty_bar + STAGES;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB16);
+        tma_prefetch_desc(&tmB32);
+        tma_prefetch_desc(&tmB64);
+        tma_prefetch_desc(&tmB128);
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tmem_full[i], 1);
+            mbar_init(&tmem_empty[i], 4);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_ptr, 2 * BN_MAX);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    const int m_slices = p.M_out / BM;
+    const int total = p.G * m_slices;
+    const int num_kb = p.K / BK;
+
+    if (warp == 0 && lane == 0) {
+        // =============================================================== TMA producer
+        if (p.wait_flags) {
+            const int epoch = p.wait_epoch + (p.epoch_base ? *p.epoch_base : 0);
+            const unsigned long long t_wait = globaltimer_ns();
+            for (int sidx = 0; sidx < p.wait_count; ++sidx)
+                if (!spin_flag_ge(p.wait_flags + sidx, epoch)) atomicOr(p.status, 1);
+            if (blockIdx.x == 0) atomicAdd(reinterpret_cast<unsigned long long*>(p.status + 2), globaltimer_ns() - t_wait);
+            fence_proxy_async_global();
+        }
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+            const int g = tile / m_slices, ms = tile - g * m_slices;
+            const int rows = __ldg(p.group_rows + g);
+            if (rows <= 0) continue;
+            const int off = __ldg(p.group_off + g);
+            for (int n0 = 0; n0 < rows; n0 += BN_MAX) {
+                const int box = box_rows_of(min(rows - n0, BN_MAX));
+                const CUtensorMap* tmB = box == 16 ? &tmB16 : (box == 32 ? &tmB32 : (box == 64 ? &tmB64 : &tmB128));
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * STAGE_BYTES;
+                    uint8_t* sb = sa + A_BYTES;
+                    const int k = kb * BK;
+                    mbar_arrive_expect_tx(&full_bar[stage], A_BYTES + box * 128);
+                    if (!A_MN) {
+                        tma_load_3d(sa, &tmA, &full_bar[stage], k, ms * BM, g);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < BM / 64; ++i)
+                            tma_load_3d(sa + i * (BK * 128), &tmA, &full_bar[stage], ms * BM + i * 64, k, g);
+                    }
+                    tma_load_2d(sb, tmB, &full_bar[stage], k, off + n0);
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // =============================================================== MMA issuer
+        constexpr uint32_t A_LBO = A_MN ? BK * 128 : 0;
+        constexpr uint32_t A_KSTEP = A_MN ? UMMA_K * 128 : UMMA_K * 2;
+        int stage = 0;
+        uint32_t phase = 0;
+        int iter = 0;
+        for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+            const int g = tile / m_slices;
+            const int rows = __ldg(p.group_rows + g);
+            if (rows <= 0) continue;
+            for (int n0 = 0; n0 < rows; n0 += BN_MAX) {
+                const int nn = min(rows - n0, BN_MAX);
+                const uint32_t n16 = static_cast<uint32_t>((nn + 15) & ~15);
+                const uint32_t idesc = make_idesc_bf16_f32(BM, n16, A_MN ? 1u : 0u, 0u);
+                const int as = iter & 1;
+                const uint32_t aphase = (iter >> 1) & 1;
+                mbar_wait(&tmem_empty[as], aphase ^ 1);
+                tcgen05_fence_after();
+                const uint32_t tmem_d = tmem_base + as * BN_MAX;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tcgen05_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+                    const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        const uint64_t da = make_smem_desc_sw128(sa + k * A_KSTEP, A_LBO, 1024);
+                        const uint64_t db = make_smem_desc_sw128(sb + k * (UMMA_K * 2), 0, 1024);
+                        umma_bf16_ss(tmem_d, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);
+                    if (kb == num_kb - 1) umma_commit(&tmem_full[as]);
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                ++iter;
+            }
+        }
+    } else if (warp >= 2) {
+        // =============================================================== epilogue: thread = output feature, column = token
+        const int lane_group = warp & 3;
+        int iter = 0;
+        for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+            const int g = tile / m_slices, ms = tile - g * m_slices;
+            const int rows = __ldg(p.group_rows + g);
+            if (rows <= 0) continue;
+            const int off = __ldg(p.group_off + g);
+            const int feat = ms * BM + lane_group * 32 + lane;
+            const float bias = p.bias ? __ldg(p.bias + static_cast<long long>(g) * p.M_out + feat) : 0.f;
+            for (int n0 = 0; n0 < rows; n0 += BN_MAX) {
+                const int nn = min(rows - n0, BN_MAX);
+                const int as = iter & 1;
+                const uint32_t aphase = (iter >> 1) & 1;
+                mbar_wait(&tmem_full[as], aphase);
+                tcgen05_fence_after();
+                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_group * 32) << 16) + as * BN_MAX;
+#pragma unroll 1
+                for (int c0 = 0; c0 < nn; c0 += 32) {
+                    uint32_t r[32];
+                    tmem_ld_32x32(taddr + c0, r);
+                    tmem_ld_wait();
+                    const int cn = min(32, nn - c0);
+                    const long long row0 = off + n0 + c0;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        if (j < cn) {
+                            float v = __uint_as_float(r[j]) + bias;
+                            if (p.residual) v += __bfloat162float(p.residual[(row0 + j) * p.ldr + feat]);
+                            p.out[(row0 + j) * p.ldo + feat] = __float2bfloat16(v);   // warp: 32 consecutive features = 64 B
+                        }
+                    }
+                }
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty[as]);
+                ++iter;
+            }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        tmem_dealloc(tmem_base, 2 * BN_MAX);
+    }
+}
+
+}  // namespace sab
+
+// =====================================================================================================================
+// fused wgrad + AMSGrad
+// =====================================================================================================================
+namespace wa {
+
+constexpr int OP_BYTES = 2 * (BK * BM * 2);              // A [64 t][128 n] + B [64 t][128 k] (two 64-wide MN atoms each)
+constexpr int SLOTS = 3;                                 // state ring per epilogue warp
+constexpr int STATE_TILE = 32 * 128;                     // 32 rows x 32 fp32 (one swizzle-128B atom group)
+constexpr int SLOT_BYTES = 4 * STATE_TILE;               // p, m, v, vmax
+constexpr int STATE_OFFSET = OP_BYTES;
+constexpr int BAR_OFFSET = STATE_OFFSET + 4 * SLOTS * SLOT_BYTES;
+constexpr int SMEM_TOTAL = BAR_OFFSET + (2 + 4 + 4 * SLOTS) * 8 + 16 + 1024;
+static_assert(SMEM_TOTAL <= 232448, "shared memory budget");
+
+struct Params {
+    int G, N, K;              // groups (slots of the segment), rows (= features of dY) and columns (= features of X) of W
+    const int* group_off;     // [G] first token row of the group in dy / x
+    const int* group_rows;    // [G] valid rows (0: the expert is not stepped)
+    const int* skip;          // optional [G, 2]: skip[2g] >= 0 -> handled by the unfused path (shadowed experts)
+    const int* step;          // [G] per-expert step count AFTER this update
+    bf16* p_bf16;             // [G, N, K] bf16 mirror consumed by the GEMMs
+    float lr, beta1, beta2, eps;
+    int amsgrad;
+};
+
+struct ChunkIter {   // enumerates (tile, 32-column chunk) of the active tiles of this CTA, in processing order
+    int tile, cc, g, mt, nt;
+    int total, tiles_per_group, n_tiles;
+    const Params* p;
+    __device__ __forceinline__ bool active(int t) {
+        const int gg = t / tiles_per_group;
+        if (__ldg(p->group_rows + gg) <= 0) return false;
+        if (p->skip && __ldg(p->skip + 2 * gg) >= 0) return false;
+        return true;
+    }
+    __device__ __forceinline__ void decode() {
+        g = tile / tiles_per_group;
+        const int r = tile - g * tiles_per_group;
+        mt = r / n_tiles;
+        nt = r - mt * n_tiles;
+    }
+    __device__ __forceinline__ void init(const Params* pp, int first, int step) {
+        p = pp;
+        n_tiles = pp->K / BN_MAX;
+        tiles_per_group = (pp->N / BM) * n_tiles;
+        total = pp->G * tiles_per_group;
+        tile = first;
+        cc = 0;
+        while (tile < total && !active(tile)) tile += step;
+        if (tile < total) decode();
+    }
+    __device__ __forceinline__ bool valid() const { return tile < total; }
+    __device__ __forceinline__ void next(int step) {
+        if (++cc == BN_MAX / 32) {
+            cc = 0;
+            tile += step;
+            while (tile < total && !active(tile)) tile += step;
+            if (tile < total) decode();
+        }
+    }
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+wgrad_adam_kernel(const Params p, const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX,
+                  const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmM,
+                  const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmVM) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* op_full = reinterpret_cast<uint64_t*>(smem + BAR_OFFSET);
+    uint64_t* op_empty = op_full + 1;
+    uint64_t* tmem_full = op_empty + 1;     // [2]
+    uint64_t* tmem_empty = tmem_full + 2;   // [2]
+    uint64_t* st_full = tmem_empty + 2;     // [4 warps][SLOTS]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(st_full + 4 * SLOTS);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmDY);
+        tma_prefetch_desc(&tmX);
+        tma_prefetch_desc(&tmP);
+        tma_prefetch_desc(&tmM);
+        tma_prefetch_desc(&tmV);
+        tma_prefetch_desc(&tmVM);
+        mbar_init(op_full, 1);
+        mbar_init(op_empty, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tmem_full[i], 1);
+            mbar_init(&tmem_empty[i], 4);
+        }
+        for (int i = 0; i < 4 * SLOTS; ++i) mbar_init(&st_full[i], 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_ptr, 2 * BN_MAX);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0 && lane == 0) {
+        // =============================================================== operand producer: dY^T / X^T k-blocks of 64 tokens
+        ChunkIter it;
+        it.init(&p, blockIdx.x, gridDim.x);
+        uint32_t phase = 0;
+        while (it.valid()) {
+            const int off = __ldg(p.group_off + it.g), rows = __ldg(p.group_rows + it.g);
+            for (int t0 = 0; t0 < rows; t0 += BK) {
+                mbar_wait(op_empty, phase ^ 1);
+                mbar_arrive_expect_tx(op_full, OP_BYTES);
+                uint8_t* sa = smem;
+                uint8_t* sb = smem + BK * BM * 2;
+#pragma unroll
+                for (int i = 0; i < BM / 64; ++i) tma_load_2d(sa + i * (BK * 128), &tmDY, op_full, it.mt * BM + i * 64, off + t0);
+#pragma unroll
+                for (int i = 0; i < BN_MAX / 64; ++i) tma_load_2d(sb + i * (BK * 128), &tmX, op_full, it.nt * BN_MAX + i * 64, off + t0);
+                phase ^= 1;
+            }
+            it.cc = BN_MAX / 32 - 1;   // jump to the next tile
+            it.next(gridDim.x);
+        }
+    } else if (warp == 1 && lane == 0) {
+        // =============================================================== MMA issuer: only ceil(rows/16) k-steps of a block
+        constexpr uint32_t idesc = make_idesc_bf16_f32(BM, BN_MAX, 1u, 1u);
+        ChunkIter it;
+        it.init(&p, blockIdx.x, gridDim.x);
+        uint32_t phase = 0;
+        int iter = 0;
+        while (it.valid()) {
+            const int rows = __ldg(p.group_rows + it.g);
+            const int as = iter & 1;
+            const uint32_t aphase = (iter >> 1) & 1;
+            mbar_wait(&tmem_empty[as], aphase ^ 1);
+            tcgen05_fence_after();
+            const uint32_t tmem_d = tmem_base + as * BN_MAX;
+            for (int t0 = 0; t0 < rows; t0 += BK) {
+                mbar_wait(op_full, phase);
+                tcgen05_fence_after();
+                const uint32_t sa = smem_u32(smem);
+                const uint32_t sb = sa + BK * BM * 2;
+                const int ksteps = min(BK / UMMA_K, (rows - t0 + UMMA_K - 1) / UMMA_K);
+                for (int k = 0; k < ksteps; ++k) {
+                    const uint64_t da = make_smem_desc_sw128(sa + k * (UMMA_K * 128), BK * 128, 1024);
+                    const uint64_t db = make_smem_desc_sw128(sb + k * (UMMA_K * 128), BK * 128, 1024);
+                    umma_bf16_ss(tmem_d, da, db, idesc, (t0 > 0 || k > 0) ? 1u : 0u);
+                }
+                umma_commit(op_empty);
+                if (t0 + BK >= rows) umma_commit(&tmem_full[as]);
+                phase ^= 1;
+            }
+            ++iter;
+            it.cc = BN_MAX / 32 - 1;
+            it.next(gridDim.x);
+        }
+    } else if (warp >= 2) {
+        // =============================================================== epilogue: state streaming + AMSGrad
+        const int q = warp & 3;                     // TMEM lane quadrant = rows [32q, 32q+32) of the tile
+        uint8_t* ring = smem + STATE_OFFSET + (warp - 2) * SLOTS * SLOT_BYTES;
+        uint64_t* full = st_full + (warp - 2) * SLOTS;
+        const int n_state = p.amsgrad ? 4 : 3;
+        auto issue_load = [&](const ChunkIter& c, int slot) {   // lane 0 only
+            uint8_t* s = ring + slot * SLOT_BYTES;
+            const int col = c.nt * BN_MAX + c.cc * 32;
+            const int row = c.g * p.N + c.mt * BM + q * 32;
+            mbar_arrive_expect_tx(&full[slot], n_state * STATE_TILE);
+            tma_load_2d(s, &tmP, &full[slot], col, row);
+            tma_load_2d(s + STATE_TILE, &tmM, &full[slot], col, row);
+            tma_load_2d(s + 2 * STATE_TILE, &tmV, &full[slot], col, row);
+            if (p.amsgrad) tma_load_2d(s + 3 * STATE_TILE, &tmVM, &full[slot], col, row);
+        };
+        ChunkIter cur, pre;
+        cur.init(&p, blockIdx.x, gridDim.x);
+        pre = cur;
+        int n_loaded = 0;   // chunks whose loads were issued
+        if (lane == 0) {
+            for (int i = 0; i < SLOTS - 1 && pre.valid(); ++i) {
+                issue_load(pre, n_loaded % SLOTS);
+                ++n_loaded;
+                pre.next(gridDim.x);
+            }
+        }
+        int c = 0, iter = 0;
+        float step_size = 0.f, inv_sqrt_bc2 = 0.f;
+        while (cur.valid()) {
+            const int slot = c % SLOTS;
+            const uint32_t sphase = (c / SLOTS) & 1;
+            const int as = iter & 1;
+            if (cur.cc == 0) {
+                const float st = static_cast<float>(__ldg(p.step + cur.g));
+                step_size = p.lr / (1.f - powf(p.beta1, st));
+                inv_sqrt_bc2 = rsqrtf(1.f - powf(p.beta2, st));
+                mbar_wait(&tmem_full[as], (iter >> 1) & 1);
+                tcgen05_fence_after();
+            }
+            if (lane == 0) {
+                // slot (c-1) % SLOTS is refilled with chunk c + SLOTS - 1: its previous contents (chunk c-1) must have been read
+                // by the TMA store engine
+                if (pre.valid()) {
+                    tma_store_wait_read<0>();
+                    issue_load(pre, n_loaded % SLOTS);
+                    ++n_loaded;
+                    pre.next(gridDim.x);
+                }
+            }
+            mbar_wait(&full[slot], sphase);
+            uint32_t r[32];
+            tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN_MAX + cur.cc * 32, r);
+            tmem_ld_wait();
+            uint8_t* s = ring + slot * SLOT_BYTES + lane * 128;
+            uint32_t packed[16];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int o = (j ^ (lane & 7)) << 4;
+                float4 pw = *reinterpret_cast<float4*>(s + o);
+                float4 m = *reinterpret_cast<float4*>(s + STATE_TILE + o);
+                float4 v = *reinterpret_cast<float4*>(s + 2 * STATE_TILE + o);
+                float4 vm = p.amsgrad ? *reinterpret_cast<float4*>(s + 3 * STATE_TILE + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+                float* pp = &pw.x; float* mp = &m.x; float* vp = &v.x; float* vmp = &vm.x;
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const float grad = __uint_as_float(r[4 * j + t]);
+                    mp[t] = mp[t] + (1.f - p.beta1) * (grad - mp[t]);
+                    vp[t] = vp[t] * p.beta2 + (1.f - p.beta2) * grad * grad;
+                    float denom;
+                    if (p.amsgrad) {
+                        vmp[t] = fmaxf(vmp[t], vp[t]);
+                        denom = sqrtf(vmp[t]) * inv_sqrt_bc2 + p.eps;
+                    } else {
+                        denom = sqrtf(vp[t]) * inv_sqrt_bc2 + p.eps;
+                    }
+                    pp[t] -= step_size * (mp[t] / denom);
+                }
+                *reinterpret_cast<float4*>(s + o) = pw;
+                *reinterpret_cast<float4*>(s + STATE_TILE + o) = m;
+                *reinterpret_cast<float4*>(s + 2 * STATE_TILE + o) = v;
+                if (p.amsgrad) *reinterpret_cast<float4*>(s + 3 * STATE_TILE + o) = vm;
+                packed[2 * j] = pack_bf16x2(pw.x, pw.y);
+                packed[2 * j + 1] = pack_bf16x2(pw.z, pw.w);
+            }
+            {   // bf16 mirror: 64 B per thread straight from registers
+                const long long row = static_cast<long long>(cur.g) * p.N + cur.mt * BM + q * 32 + lane;
+                int4* dst = reinterpret_cast<int4*>(p.p_bf16 + row * p.K + cur.nt * BN_MAX + cur.cc * 32);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    dst[j] = make_int4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                uint8_t* sb = ring + slot * SLOT_BYTES;
+                const int col = cur.nt * BN_MAX + cur.cc * 32;
+                const int row = cur.g * p.N + cur.mt * BM + q * 32;
+                tma_store_2d(&tmP, sb, col, row);
+                tma_store_2d(&tmM, sb + STATE_TILE, col, row);
+                tma_store_2d(&tmV, sb + 2 * STATE_TILE, col, row);
+                if (p.amsgrad) tma_store_2d(&tmVM, sb + 3 * STATE_TILE, col, row);
+                tma_store_commit();
+            }
+            if (cur.cc == BN_MAX / 32 - 1) {   // accumulator fully drained
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty[as]);
+                ++iter;
+            }
+            ++c;
+            cur.next(gridDim.x);
+        }
+        if (lane == 0) tma_store_wait<0>();   // all state tiles are in global memory before the CTA exits
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        tmem_dealloc(tmem_base, 2 * BN_MAX);
+    }
+}
+
+}  // namespace wa
+}  // namespace smallm
+}  // namespace lah
+
+using namespace lah;
+using namespace lah::smallm;
+
+extern "C" const int* lah_get_epoch_base();
+
+extern "C" {
+
+// out[row, :] = act_rows[row, :] @ W[g]^T (+bias[g]) (+residual[row, :]) for the rows of every group, swap-AB tiles.
+//   a_mn == 0: W is [G, M_out, K] (forward);  a_mn == 1: W is [G, K, M_out] and the product is x @ W (dgrad)
+int lah_swapab_linear(const void* x, long long ldx, int x_rows, const void* W, int G, int M_out, int K, int a_mn,
+                      void* out, long long ldo, const int* group_off, const int* group_rows, const float* bias,
+                      const void* residual, long long ldr, const int* wait_flags, int wait_count, int wait_epoch,
+                      const int* epoch_base, int* status, int max_ctas, cudaStream_t st) {
+    if ((K % BK) || (M_out % BM) || (ldx % 8)) return -2;
+    CUtensorMap tmA, tmB[4];
+    if (!a_mn) {
+        uint64_t dims[3] = {(uint64_t)K, (uint64_t)M_out, (uint64_t)G};
+        uint64_t str[2] = {(uint64_t)K * 2, (uint64_t)M_out * K * 2};
+        uint32_t box[3] = {BK, BM, 1};
+        int r = make_tmap(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, W, 3, dims, str, box);
+        if (r) return r;
+    } else {
+        uint64_t dims[3] = {(uint64_t)M_out, (uint64_t)K, (uint64_t)G};
+        uint64_t str[2] = {(uint64_t)M_out * 2, (uint64_t)M_out * K * 2};
+        uint32_t box[3] = {64, BK, 1};
+        int r = make_tmap(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, W, 3, dims, str, box);
+        if (r) return r;
+    }
+    const uint32_t boxes[4] = {16, 32, 64, 128};
+    for (int i = 0; i < 4; ++i) {
+        uint64_t dims[2] = {(uint64_t)K, (uint64_t)x_rows};
+        uint64_t str[1] = {(uint64_t)ldx * 2};
+        uint32_t box[2] = {BK, boxes[i]};
+        int r = make_tmap(&tmB[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, x, 2, dims, str, box);
+        if (r) return r;
+    }
+    sab::Params p;
+    p.G = G; p.M_out = M_out; p.K = K; p.group_off = group_off; p.group_rows = group_rows; p.out = (bf16*)out; p.ldo = ldo;
+    p.bias = bias; p.residual = (const bf16*)residual; p.ldr = ldr; p.wait_flags = wait_flags; p.wait_count = wait_count;
+    p.wait_epoch = wait_epoch; p.epoch_base = epoch_base ? epoch_base : lah_get_epoch_base(); p.status = status;
+    const int total = G * (M_out / BM);
+    if (total <= 0) return 0;
+    int ctas = num_sms();
+    if (max_ctas > 0 && max_ctas < ctas) ctas = max_ctas;
+    if (total < ctas) ctas = total;
+    static bool configured[2] = {false, false};
+    if (!a_mn) {
+        if (!configured[0]) {
+            cudaError_t e = cudaFuncSetAttribute(sab::swapab_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sab::SMEM_TOTAL);
+            if (e != cudaSuccess) return -(int)e;
+            configured[0] = true;
+        }
+        sab::swapab_kernel<false><<<ctas, NUM_THREADS, sab::SMEM_TOTAL, st>>>(p, tmA, tmB[0], tmB[1], tmB[2], tmB[3]);
+    } else {
+        if (!configured[1]) {
+            cudaError_t e = cudaFuncSetAttribute(sab::swapab_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sab::SMEM_TOTAL);
+            if (e != cudaSuccess) return -(int)e;
+            configured[1] = true;
+        }
+        sab::swapab_kernel<true><<<ctas, NUM_THREADS, sab::SMEM_TOTAL, st>>>(p, tmA, tmB[0], tmB[1], tmB[2], tmB[3]);
+    }
+    return -(int)cudaGetLastError();
+}
+
+// W[g] -= AMSGrad(dW[g] = dy_g^T x_g) for every group with rows > 0; p / m / v / vmax are [G, N, K] fp32, p_bf16 the mirror
+int lah_wgrad_adam(const void* dy, long long lddy, const void* x, long long ldx, int total_rows, int G, int N, int K,
+                   const int* group_off, const int* group_rows, const int* skip, const int* step, float* p, float* m,
+                   float* v, float* vmax, void* p_bf16, float lr, float beta1, float beta2, float eps, int amsgrad,
+                   int max_ctas, cudaStream_t st) {
+    if ((N % BM) || (K % BN_MAX) || (lddy % 8) || (ldx % 8)) return -2;
+    CUtensorMap tmDY, tmX, tmS[4];
+    {
+        uint64_t dims[2] = {(uint64_t)N, (uint64_t)total_rows};
+        uint64_t str[1] = {(uint64_t)lddy * 2};
+        uint32_t box[2] = {64, BK};
+        int r = make_tmap(&tmDY, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dy, 2, dims, str, box);
+        if (r) return r;
+    }
+    {
+        uint64_t dims[2] = {(uint64_t)K, (uint64_t)total_rows};
+        uint64_t str[1] = {(uint64_t)ldx * 2};
+        uint32_t box[2] = {64, BK};
+        int r = make_tmap(&tmX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, x, 2, dims, str, box);
+        if (r) return r;
+    }
+    float* states[4] = {p, m, v, amsgrad ? vmax : p};
+    for (int i = 0; i < 4; ++i) {
+        uint64_t dims[2] = {(uint64_t)K, (uint64_t)G * N};
+        uint64_t str[1] = {(uint64_t)K * 4};
+        uint32_t box[2] = {32, 32};
+        int r = make_tmap(&tmS[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, states[i], 2, dims, str, box);
+        if (r) return r;
+    }
+    wa::Params a;
+    a.G = G; a.N = N; a.K = K; a.group_off = group_off; a.group_rows = group_rows; a.skip = skip; a.step = step;
+    a.p_bf16 = (bf16*)p_bf16; a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.amsgrad = amsgrad;
+    const long long total = 1ll * G * (N / BM) * (K / BN_MAX);
+    if (total <= 0) return 0;
+    int ctas = num_sms();
+    if (max_ctas > 0 && max_ctas < ctas) ctas = max_ctas;
+    if (total < ctas) ctas = (int)total;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(wa::wgrad_adam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wa::SMEM_TOTAL);
+        if (e != cudaSuccess) return -(int)e;
+        configured = true;
+    }
+    wa::wgrad_adam_kernel<<<ctas, NUM_THREADS, wa::SMEM_TOTAL, st>>>(a, tmDY, tmX, tmS[0], tmS[1], tmS[2], tmS[3]);
+    return -(int)cudaGetLastError();
+}
+
+}  // extern "C"

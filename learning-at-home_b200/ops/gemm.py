@@ -38,7 +38,7 @@ def _lib():
                                          c_int, c_void_p]
         lib.lah_gemm_kgroup2.restype = c_int
         lib.lah_gemm_kgroup2.argtypes = [c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p,
-                                         c_void_p, c_ll, c_ll, c_int, c_void_p]
+                                         c_void_p, c_ll, c_ll, c_int, c_int, c_void_p]
         _configured = True
     return lib
 
@@ -107,7 +107,7 @@ def grouped_linear(a, w, *, tile_group=None, bias=None, residual=None, w_is_kn=F
     return out
 
 
-def grouped_wgrad(dy, x, group_off, num_groups, *, out=None, block_n=None, max_ctas=0, two_cta=False):
+def grouped_wgrad(dy, x, group_off, num_groups, *, out=None, block_n=None, max_ctas=0, two_cta=False, accumulate=False):
     """
     out[g] = dy[off[g]:off[g+1]]^T @ x[off[g]:off[g+1]]   (fp32 [G, M, N]); groups with no rows are left untouched.
     The reduction over an expert's rows IS the gradient reduction over all trainers that routed tokens to it.
@@ -122,10 +122,11 @@ def grouped_wgrad(dy, x, group_off, num_groups, *, out=None, block_n=None, max_c
     assert out.dtype == torch.float32 and out.is_contiguous()
     if two_cta and M % 256 == 0 and N % 256 == 0:
         code = _lib().lah_gemm_kgroup2(ptr(dy), dy.stride(0), ptr(x), x.stride(0), rows, num_groups, M, N,
-                                       ptr(group_off), ptr(out), N, M * N, max_ctas, stream_ptr())
+                                       ptr(group_off), ptr(out), N, M * N, max_ctas, int(accumulate), stream_ptr())
         native.check(code, "lah_gemm_kgroup2")
         native.count_launch()
         return out
+    assert not accumulate, "gradient accumulation is implemented in the CTA-pair kernel (two_cta=True)"
     bn = block_n or _pick_block_n(N)
     code = _lib().lah_gemm_kgroup(ptr(dy), dy.stride(0), ptr(x), x.stride(0), rows, num_groups, M, N, ptr(group_off),
                                   ptr(out), N, M * N, bn, max_ctas, stream_ptr())

@@ -27,20 +27,28 @@ def _lib():
     P, I, L, Fl = c_void_p, c_int, c_ll, c_float
     sigs = {
         "lah_ln_relu_fwd": [P, P, P, P, P, P, P, I, I, I, P],
+        "lah_ln_relu_fwd_t": [P, P, P, P, P, P, P, I, I, I, I, P],
+        "lah_ln_relu_bwd_t": [P, P, P, P, P, P, P, P, P, P, P, I, I, I, I, P],
+        "lah_grouped_colsum_t": [P, L, P, I, P, I, I, P],
+        "lah_set_step_counters": [P],
+        "lah_set_spin_timeout_ms": [I],
+        "lah_step_begin": [I, L, P],
+        "lah_swapab_linear": [P, L, I, P, I, I, I, I, P, L, P, P, P, P, L, P, I, I, P, P, I, P],
+        "lah_wgrad_adam": [P, L, P, L, I, I, I, I, P, P, P, P, P, P, P, P, P, Fl, Fl, Fl, Fl, I, I, P],
         "lah_ln_relu_fwd_q": [P, P, P, P, P, P, P, I, I, I, P, P, P],
         "lah_ln_relu_bwd": [P, P, P, P, P, P, P, P, P, P, P, I, I, I, P],
         "lah_grouped_colsum": [P, L, P, I, P, I, P],
         "lah_set_peers": [P, I, I],
         "lah_set_wait_counter": [P],
         "lah_gate_topk": [P, I, P, I, I, P, Fl, c_ull, L, P, P, P, P, P],
-        "lah_layout_exchange": [L, L, I, I, I, I, I, I, P, P, P, P, P, P, P, I, Fl, I, P, P, P, P, P],
+        "lah_layout_exchange": [L, L, I, I, I, I, I, I, I, P, P, P, P, P, P, P, I, Fl, I, P, P, P, P, P],
         "lah_scatter_rows": [P, P, P, P, P, P, L, L, I, I, I, I, I, I, I, I, P, P, P, P, P, I, P],
         "lah_pull_shadow": [P, I, I, L, L, I, P, I, P],
         "lah_zero_slots": [P, I, P, I, I, I, I, P],
         "lah_signal_wait": [L, I, I, I, I, P, P],
         "lah_combine_rows": [L, P, P, P, P, I, I, I, I, L, I, I, I, I, P, P, P],
         "lah_gate_bwd": [L, P, P, P, P, P, I, I, I, I, P, I, P, P],
-        "lah_adam_step": [P, P, P, P, P, P, I, P, I, P, P, I, Fl, Fl, Fl, Fl, Fl, I, I, I, L, P, Fl, I, P, L, I, P],
+        "lah_adam_step": [P, P, P, P, P, P, I, P, I, P, P, I, Fl, Fl, Fl, Fl, Fl, I, I, I, L, P, Fl, I, P, L, I, I, P],
         "lah_bump_steps": [P, P, I, P],
         "lah_cast_bf16": [P, P, L, P],
         "lah_attention_fwd": [P, P, I, I, I, P],
@@ -66,7 +74,7 @@ def _grid_array(grid_size):
 # ---------------------------------------------------------------------------------------------------------
 # LayerNorm + ReLU over expert-grouped rows
 # ---------------------------------------------------------------------------------------------------------
-def ln_relu_fwd(h, gamma, beta, tile_group, *, out, mean, rstd, relu=True, quant=None):
+def ln_relu_fwd(h, gamma, beta, tile_group, *, out, mean, rstd, relu=True, quant=None, tile_rows=128):
     """:param quant: optional ops.fp8.MXFP8Tensor that additionally receives the output as an MXFP8 GEMM operand
     (``out`` may then be None: forward-only runs do not need the bf16 copy)"""
     rows, C = h.shape
@@ -77,26 +85,27 @@ def ln_relu_fwd(h, gamma, beta, tile_group, *, out, mean, rstd, relu=True, quant
                                               ptr(tile_group), rows, C, int(relu), ptr(quant.q), ptr(quant.sf),
                                               stream_ptr()), "lah_ln_relu_fwd_q")
     else:
-        native.check(_lib().lah_ln_relu_fwd(ptr(h), ptr(out), ptr(mean), ptr(rstd), ptr(gamma), ptr(beta),
-                                            ptr(tile_group), rows, C, int(relu), stream_ptr()), "lah_ln_relu_fwd")
+        native.check(_lib().lah_ln_relu_fwd_t(ptr(h), ptr(out), ptr(mean), ptr(rstd), ptr(gamma), ptr(beta),
+                                              ptr(tile_group), rows, C, int(relu), int(tile_rows), stream_ptr()),
+                     "lah_ln_relu_fwd")
     native.count_launch()
     return out
 
 
-def ln_relu_bwd(da, h, mean, rstd, gamma, beta, tile_group, *, dh, dgamma, dbeta, dbias, relu=True):
+def ln_relu_bwd(da, h, mean, rstd, gamma, beta, tile_group, *, dh, dgamma, dbeta, dbias, relu=True, tile_rows=128):
     rows, C = h.shape
     assert da.is_contiguous() and h.is_contiguous() and dh.is_contiguous()
-    native.check(_lib().lah_ln_relu_bwd(ptr(da), ptr(h), ptr(mean), ptr(rstd), ptr(gamma), ptr(beta), ptr(dh),
-                                        ptr(dgamma), ptr(dbeta), ptr(dbias), ptr(tile_group), rows, C, int(relu),
-                                        stream_ptr()), "lah_ln_relu_bwd")
+    native.check(_lib().lah_ln_relu_bwd_t(ptr(da), ptr(h), ptr(mean), ptr(rstd), ptr(gamma), ptr(beta), ptr(dh),
+                                          ptr(dgamma), ptr(dbeta), ptr(dbias), ptr(tile_group), rows, C, int(relu),
+                                          int(tile_rows), stream_ptr()), "lah_ln_relu_bwd")
     native.count_launch()
     return dh
 
 
-def grouped_colsum(x, tile_group, *, out):
+def grouped_colsum(x, tile_group, *, out, tile_rows=128):
     rows, C = x.shape
-    native.check(_lib().lah_grouped_colsum(ptr(x), x.stride(0), ptr(out), C, ptr(tile_group), rows, stream_ptr()),
-                 "lah_grouped_colsum")
+    native.check(_lib().lah_grouped_colsum_t(ptr(x), x.stride(0), ptr(out), C, ptr(tile_group), rows, int(tile_rows),
+                                             stream_ptr()), "lah_grouped_colsum")
     native.count_launch()
     return out
 
@@ -114,6 +123,23 @@ def set_wait_counter(counter):
     native.check(_lib().lah_set_wait_counter(ptr(counter)), "lah_set_wait_counter")
 
 
+def set_step_counters(ctr):
+    """int32 device tensor [4]: [0] epoch base added to every step-relative epoch, [2:4] int64 token base of the gate's
+    failure-injection stream (None disables).  Nothing that changes from step to step is then a kernel ARGUMENT, so a
+    whole training step can be captured in a CUDA graph and replayed."""
+    native.check(_lib().lah_set_step_counters(ptr(ctr)), "lah_set_step_counters")
+
+
+def step_begin(epoch_delta, token_delta=0):
+    native.check(_lib().lah_step_begin(int(epoch_delta), int(token_delta), stream_ptr()), "lah_step_begin")
+    native.count_launch()
+
+
+def set_spin_timeout_ms(ms):
+    """timeout of every peer-flag wait (0 = ~10 s); on expiry the waiter raises STATUS_TIMEOUT and CONTINUES"""
+    native.check(_lib().lah_set_spin_timeout_ms(int(ms)), "lah_set_spin_timeout_ms")
+
+
 def gate_topk(logits, grid_size, k, *, alive=None, failure_rate=0.0, seed=0, token_offset=0, idx, w, pos, counts):
     B = logits.shape[0]
     assert logits.dtype == torch.float32 and logits.is_contiguous() and logits.shape[1] == sum(grid_size)
@@ -123,11 +149,12 @@ def gate_topk(logits, grid_size, k, *, alive=None, failure_rate=0.0, seed=0, tok
     native.count_launch()
 
 
-def layout_exchange(cnt_all_off, flags_off, slot, epoch, E, E_loc, max_rows, *, align=128, counts, dst_row, group_off, group_rows,
+def layout_exchange(cnt_all_off, flags_off, slot, epoch, E, E_loc, max_rows, *, align=128, tile_rows=None, counts, dst_row, group_off, group_rows,
                     tile_group, total_rows, status, shadow_slots=0, shadow_tol=1.1, min_shadow_rows=512, route_owner=None,
                     step_rows=None, shadow_info=None, owned_shadow=None):
     """count exchange + global layout; with ``shadow_slots`` > 0 also the hot-expert shadow selection (csrc/moe.cu)"""
-    native.check(_lib().lah_layout_exchange(cnt_all_off, flags_off, slot, epoch, E, E_loc, max_rows, align, ptr(counts),
+    native.check(_lib().lah_layout_exchange(cnt_all_off, flags_off, slot, epoch, E, E_loc, max_rows, align,
+                                            int(tile_rows or min(align, 128)), ptr(counts),
                                             ptr(dst_row), ptr(group_off), ptr(group_rows), ptr(tile_group),
                                             ptr(total_rows), ptr(status), int(shadow_slots), float(shadow_tol),
                                             int(min_shadow_rows), ptr(route_owner), ptr(step_rows), ptr(shadow_info),
@@ -228,7 +255,8 @@ def attention_ref(qkv, num_heads, seq_len=512):
 # ---------------------------------------------------------------------------------------------------------
 def adam_step(p, g, m, v, vmax, p_bf16, seg_sizes, G, *, step=None, group_rows=None, step_scalar=0, lr=1e-3,
               betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, amsgrad=True, zero_mask=0, world=1,
-              peer_grad_off=-1, peer_bases=None, grad_scale=1.0, G_active=0, shadow_of=None, shadow_g_off=-1, me=0):
+              peer_grad_off=-1, peer_bases=None, grad_scale=1.0, G_active=0, shadow_of=None, shadow_g_off=-1, me=0,
+              seg_mask=0):
     arr = None
     if peer_bases is not None:
         arr = (c_ull * len(peer_bases))(*[int(b) for b in peer_bases])
@@ -248,8 +276,64 @@ def adam_step(p, g, m, v, vmax, p_bf16, seg_sizes, G, *, step=None, group_rows=N
                                       ptr(group_rows), int(step_scalar), lr, betas[0], betas[1], eps, weight_decay,
                                       int(amsgrad), int(zero_mask), world, peer_grad_off,
                                       ctypes.cast(arr, c_void_p) if arr is not None else c_void_p(0), grad_scale,
-                                      int(G_active), ptr(shadow_of), int(shadow_g_off), int(me),
+                                      int(G_active), ptr(shadow_of), int(shadow_g_off), int(me), int(seg_mask),
                                       stream_ptr()), "lah_adam_step")
+    native.count_launch()
+
+
+def swapab_linear(x, w, group_off, group_rows, *, out, bias=None, residual=None, w_is_kn=False, wait=None, max_ctas=0):
+    """
+    Small-M grouped linear on swap-AB tcgen05 tiles (csrc/small_m.cu): for the rows [group_off[g], +group_rows[g]) of every
+    group, out = x @ W[g]^T (+bias[g]) (+residual)   (w_is_kn: out = x @ W[g], the dgrad of a Linear whose weight is W).
+    Weights are streamed exactly once per 128 tokens; a group of r rows costs MMAs of N = ceil16(r).
+    :param x: [rows, K] bf16;  w: [G, M_out, K] (or [G, K, M_out] with w_is_kn) bf16;  out: [rows, M_out] bf16
+    """
+    assert x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and out.dtype == torch.bfloat16 and w.is_contiguous()
+    rows, K = x.shape
+    G = w.shape[0]
+    M_out = w.shape[2] if w_is_kn else w.shape[1]
+    assert (w.shape[1] if w_is_kn else w.shape[2]) == K and x.stride(1) == 1 and out.stride(1) == 1
+    wait_flags, wait_count, wait_epoch, wait_status = (wait[0], wait[0].numel(), wait[1], wait[2]) if wait else (None, 0, 0, None)
+    native.check(_lib().lah_swapab_linear(ptr(x), x.stride(0), rows, ptr(w), G, M_out, K, int(w_is_kn), ptr(out),
+                                          out.stride(0), ptr(group_off), ptr(group_rows), ptr(bias), ptr(residual),
+                                          residual.stride(0) if residual is not None else 0, ptr(wait_flags), wait_count,
+                                          wait_epoch, c_void_p(0), ptr(wait_status), int(max_ctas), stream_ptr()),
+                 "lah_swapab_linear")
+    native.count_launch()
+    return out
+
+
+def swapab_linear_ref(x, w, group_off, group_rows, *, bias=None, residual=None, w_is_kn=False):
+    off, rows = group_off.tolist(), group_rows.tolist()
+    M_out = w.shape[2] if w_is_kn else w.shape[1]
+    out = torch.zeros(x.shape[0], M_out, dtype=torch.float32, device=x.device)
+    for g, (o, r) in enumerate(zip(off, rows)):
+        if r <= 0:
+            continue
+        wg = w[g].float()
+        y = x[o:o + r].float() @ (wg if w_is_kn else wg.t())
+        if bias is not None:
+            y = y + bias.view(w.shape[0], M_out)[g]
+        if residual is not None:
+            y = y + residual[o:o + r].float()
+        out[o:o + r] = y
+    return out
+
+
+def wgrad_adam(dy, x, group_off, group_rows, *, p, m, v, vmax, p_bf16, step, skip=None, lr=1e-3, betas=(0.9, 0.999),
+               eps=1e-8, amsgrad=True, max_ctas=0):
+    """
+    Fused weight gradient + per-expert AMSGrad (csrc/small_m.cu): for every group g with rows > 0,
+    dW[g] = dy_g^T x_g is formed in TMEM and applied to p / m / v / vmax ([G, N, K] fp32) and the bf16 mirror in the same
+    kernel; the gradient never reaches HBM.  ``step`` holds the per-expert step counts AFTER this update.
+    """
+    G, N, Kd = p.shape
+    assert dy.shape[1] == N and x.shape[1] == Kd and dy.shape[0] == x.shape[0] and p.is_contiguous()
+    assert dy.dtype == torch.bfloat16 and x.dtype == torch.bfloat16 and p.dtype == torch.float32
+    native.check(_lib().lah_wgrad_adam(ptr(dy), dy.stride(0), ptr(x), x.stride(0), dy.shape[0], G, N, Kd, ptr(group_off),
+                                       ptr(group_rows), ptr(skip), ptr(step), ptr(p), ptr(m), ptr(v), ptr(vmax),
+                                       ptr(p_bf16), lr, betas[0], betas[1], eps, int(amsgrad), int(max_ctas),
+                                       stream_ptr()), "lah_wgrad_adam")
     native.count_launch()
 
 

@@ -68,6 +68,35 @@ class DMoEConfig:
     # "bf16" or "fp8": with "fp8" the three forward GEMMs of every expert run on block-scaled FP8 tensor cores (MXFP8:
     # E4M3 + UE8M0 scale per 1x32 block, csrc/grouped_gemm_fp8.cu); dgrad / wgrad / optimizer are unchanged (bf16 / fp32)
     expert_dtype: str = "bf16"
+    # which expert kernels run (csrc/):
+    #   "big":   rows grouped per expert and padded to 256-row CTA-pair tiles (grouped_gemm_2cta.cu) — compute-bound regime
+    #   "small": the reference's operating point (64 trainers x batch 4 => O(16) rows per expert): swap-AB tcgen05 tiles
+    #            that stream every weight once (small_m.cu), groups padded to 16 rows, weight gradient + AMSGrad fused in
+    #            one kernel (the gradient never reaches HBM)
+    #   "auto":  "small" when a step brings fewer than 128 rows per expert on average
+    expert_path: str = "auto"
+    # asynchronous expert updates (reference: EmulatedDMoE.update_every_inputs / update_every_steps,
+    # experiments/convergence/dmoe_emulator.py:70-77): an expert accumulates weight gradients and steps once it has seen
+    # >= update_every_inputs rows or >= update_every_steps steps since its first pending row.  (0, 0) = step after every
+    # backward batch (lib/runtime/expert_backend.py:95-97), the default.
+    update_every_inputs: int = 0
+    update_every_steps: int = 0
+    # peer-flag wait timeout in ms (0 = ~10 s).  On expiry the waiting rank marks the step degraded (status bit) and goes on
+    # with whatever arrived — the fused-path analogue of run_and_await_k's timeout_after_k_min (lib/utils/threading.py:76-125)
+    peer_timeout_ms: int = 0
+
+    def resolved_path(self, world: int = 1) -> str:
+        if self.accumulate:
+            return "big"      # gradient accumulation across steps needs the weight gradient in HBM (unfused wgrad + AMSGrad)
+        if self.expert_path != "auto":
+            return self.expert_path
+        rows_per_expert = self.tokens_per_rank * world * self.k / max(1, self.num_experts)
+        return "small" if (rows_per_expert < 128 and self.expert_dtype == "bf16" and self.inner % 128 == 0
+                           and self.hidden % 128 == 0) else "big"
+
+    @property
+    def accumulate(self) -> bool:
+        return self.update_every_inputs > 1 or self.update_every_steps > 1
 
     @property
     def num_experts(self) -> int:
@@ -112,13 +141,22 @@ class EngineContext:
         pairs = cfg.tokens_per_rank * cfg.k
         cap = pairs if self.world == 1 else int(math.ceil(pairs * cfg.capacity_factor))
         import os
-        self.two_cta = cfg.two_cta and os.environ.get("LAH_TWO_CTA", "1") != "0" and cfg.inner % 256 == 0 \
-            and cfg.hidden % 256 == 0
-        self.align = 256 if self.two_cta else 128   # expert groups are padded to this many rows
-        self.S = min(int(cfg.shadow_experts), 2 * K.MAX_WORLD) if self.world > 1 else 0   # shadow slots per rank / layer
+        self.small = cfg.resolved_path(self.world) == "small"
+        if self.small:
+            # weight-streaming regime: hot-expert replicas would move 12.6 MB of weights to save a few rows -> static placement
+            self.two_cta = False
+            self.align = self.tile_rows = 16
+            self.S = 0
+        else:
+            self.two_cta = cfg.two_cta and os.environ.get("LAH_TWO_CTA", "1") != "0" and cfg.inner % 256 == 0 \
+                and cfg.hidden % 256 == 0
+            self.align = 256 if self.two_cta else 128   # expert groups are padded to this many rows
+            self.tile_rows = 128
+            self.S = min(int(cfg.shadow_experts), 2 * K.MAX_WORLD) if self.world > 1 else 0   # shadow slots per rank / layer
         self.G_tot = self.E_loc + self.S
         self.max_rows = ((cap + self.align - 1) // self.align + self.G_tot) * self.align
-        self.max_tiles = self.max_rows // 128
+        self.max_rows = (self.max_rows + 127) // 128 * 128
+        self.max_tiles = self.max_rows // self.tile_rows
         H = cfg.hidden
         sym_rows_bytes = self.max_rows * H * 2
         need = (2 * cfg.num_layers + 2) * (sym_rows_bytes + 4096) + K.MAX_WORLD * self.E * 4 + (32 << 20)
@@ -137,6 +175,12 @@ class EngineContext:
         self.status = self._status_buf[:1]
         self.wait_ns = self._status_buf[2:4].view(torch.int64)
         K.set_wait_counter(self.wait_ns)
+        # device-resident step counters: epochs / token offsets passed to the kernels are RELATIVE to them, so a captured
+        # CUDA graph of a whole step stays valid from one replay to the next (see csrc/moe.cu Peers::step_ctr)
+        self.step_ctr = torch.zeros(4, **i32)
+        K.set_step_counters(self.step_ctr)
+        K.set_spin_timeout_ms(cfg.peer_timeout_ms)
+        assert 2 * cfg.num_layers + 4 < self.EPOCH_STRIDE
         self.alive = torch.ones(self.E, dtype=torch.uint8, device=self.device)
         self.epoch = 0
         self.token_counter = 0
@@ -150,13 +194,26 @@ class EngineContext:
         self.dh = torch.empty(self.max_rows, cfg.inner, **bf)
         self.heap.barrier()
 
+    EPOCH_STRIDE = 64   # epochs a step may consume; the device-side base advances by this much per begin_step()
+
     def close(self):
         """release the symmetric heap (peer mappings + the arena); idempotent.  All tensors carved out of the heap become
         invalid, so call it only when the trainer / layers of this context are no longer used."""
         K.set_wait_counter(None)
+        K.set_step_counters(None)
         self.heap.close()
 
+    def begin_step(self):
+        """advance the device-side epoch / token bases (one tiny kernel) and restart the step-relative counters; called at
+        the top of every training / evaluation step by ALL ranks (collective by construction: every rank runs the same
+        program).  Inside a captured CUDA graph the bump is part of the graph."""
+        K.step_begin(self.EPOCH_STRIDE, self.cfg.num_layers * self.cfg.tokens_per_rank)
+        self.epoch = 0
+        self.token_counter = 0
+
     def next_epoch(self) -> int:
+        if self.epoch + 1 >= self.EPOCH_STRIDE:   # a caller that never begins steps (layer-level tests) wraps here
+            self.begin_step()
         self.epoch += 1
         return self.epoch
 
@@ -208,13 +265,24 @@ class ExpertShard:
         self.views: Dict[str, torch.Tensor] = {}
         self.grads: Dict[str, torch.Tensor] = {}
         self.bf16: Dict[str, torch.Tensor] = {}
+        self.m_views: Dict[str, torch.Tensor] = {}
+        self.v_views: Dict[str, torch.Tensor] = {}
+        self.vmax_views: Dict[str, torch.Tensor] = {}
         off = 0
         for name, size in zip(SEG_NAMES, self.seg_sizes):
             sl = slice(off, off + size * slots)
             self.views[name] = self.p[sl].view(slots, *shapes[name])
             self.grads[name] = self.g[sl].view(slots, *shapes[name])
             self.bf16[name] = self.p_bf16[sl].view(slots, *shapes[name])
+            self.m_views[name] = self.m[sl].view(slots, *shapes[name])
+            self.v_views[name] = self.v[sl].view(slots, *shapes[name])
+            if self.vmax is not None:
+                self.vmax_views[name] = self.vmax[sl].view(slots, *shapes[name])
             off += size * slots
+        # asynchronous-update bookkeeping (DMoEConfig.update_every_*): rows / steps pending since the last optimizer step
+        self.pending_rows = torch.zeros(E_loc, dtype=torch.int32, device=device)
+        self.pending_steps = torch.zeros(E_loc, dtype=torch.int32, device=device)
+        self.fire = torch.zeros(E_loc, dtype=torch.int32, device=device)
         self.w8 = None        # MXFP8 copies of w1/w2/w3 (expert_dtype == "fp8"), refreshed lazily from the bf16 mirror
         self.w8_dirty = True
         if cfg.expert_dtype == "fp8" and ctx is not None:
@@ -339,6 +407,7 @@ class LayerWorkspace:
         self.owned_shadow = torch.full((ctx.E_loc * 2,), -1, **i32)
         self.tile_group = torch.full((ctx.max_tiles,), -1, **i32)
         self.total_rows = torch.zeros(1, **i32)
+        self.outstanding = False   # a training-mode forward whose backward has not run yet owns this workspace
 
 
 # =========================================================================================================
@@ -349,11 +418,21 @@ class _FusedDMoEFunction(torch.autograd.Function):
     def forward(ctx, x, logits, layer):
         ctx.layer = layer
         ctx.B = x.shape[0]
+        ws = layer.ws
+        if ws.outstanding:
+            raise RuntimeError("FusedDMoE: forward() called again before the backward of the previous training-mode forward "
+                               "(activations of a layer are single-buffered; run evaluate() / the next micro-batch after "
+                               "backward, or call layer.release_workspace() to drop the pending forward)")
+        ctx.tracked = bool(x.requires_grad or logits.requires_grad)
+        ws.outstanding = ctx.tracked
         return layer._forward_cuda(x, logits)
 
     @staticmethod
     def backward(ctx, grad_out):
+        if not ctx.layer.ws.outstanding:
+            raise RuntimeError("FusedDMoE: backward() without a pending forward (the workspace was released or reused)")
         dx, dlogits = ctx.layer._backward_cuda(grad_out.contiguous(), ctx.B)
+        ctx.layer.ws.outstanding = False
         return dx, dlogits, None
 
 
@@ -412,6 +491,11 @@ class FusedDMoE(nn.Module):
         assert x.shape[0] <= self.cfg.tokens_per_rank, "batch exceeds DMoEConfig.tokens_per_rank"
         return _FusedDMoEFunction.apply(x.to(torch.bfloat16).contiguous(), logits.contiguous(), self)
 
+    def release_workspace(self):
+        """forget a training-mode forward whose backward will never run (e.g. an exception between forward and backward)"""
+        if self.ws is not None:
+            self.ws.outstanding = False
+
     # ------------------------------------------------------------------ sm_100a path
     def _forward_cuda(self, x, logits):
         c, ws, sh, cfg = self.ctx, self.ws, self.shard, self.cfg
@@ -425,7 +509,7 @@ class FusedDMoE(nn.Module):
         c.token_counter += B
         c.timer.mark("gate_topk")
         K.layout_exchange(c.cnt_all_off, c.flags_off, K.SLOT_COUNTS, epoch, c.E, c.E_loc, c.max_rows, align=c.align,
-                          counts=c.counts,
+                          tile_rows=c.tile_rows, counts=c.counts,
                           dst_row=ws.dst_row, group_off=ws.group_off, group_rows=ws.group_rows,
                           tile_group=ws.tile_group, total_rows=ws.total_rows, status=c.status, shadow_slots=c.S,
                           shadow_tol=cfg.shadow_tol, min_shadow_rows=cfg.shadow_min_rows, route_owner=ws.route_owner,
@@ -441,7 +525,15 @@ class FusedDMoE(nn.Module):
         # producer polls the peers' dispatch flags itself (no separate wait kernel)
         tg = ws.tile_group
         wait = (c.flags[K.SLOT_DISPATCH, :c.world], epoch, c.status) if c.world > 1 else None
-        if cfg.expert_dtype == "fp8":
+        if c.small:
+            # weight-streaming regime: swap-AB tiles (weights on MMA-M, the group's 16..128 tokens on MMA-N), groups of 16 rows
+            go, gr_, T = ws.group_off, ws.group_rows, c.tile_rows
+            K.swapab_linear(ws.xd, sh.bf16["w1"], go, gr_, out=ws.h1, bias=sh.views["b1"], wait=wait)
+            K.ln_relu_fwd(ws.h1, sh.views["g1"], sh.views["be1"], tg, out=ws.a1, mean=ws.mean1, rstd=ws.rstd1, tile_rows=T)
+            K.swapab_linear(ws.a1, sh.bf16["w2"], go, gr_, out=ws.h2, bias=sh.views["b2"])
+            K.ln_relu_fwd(ws.h2, sh.views["g2"], sh.views["be2"], tg, out=ws.a2, mean=ws.mean2, rstd=ws.rstd2, tile_rows=T)
+            K.swapab_linear(ws.a2, sh.bf16["w3"], go, gr_, out=ws.yo, bias=sh.views["b3"], residual=ws.xd)
+        elif cfg.expert_dtype == "fp8":
             self._expert_ffn_fp8(wait, epoch)
         else:
             gemm.grouped_linear(ws.xd, sh.bf16["w1"], tile_group=tg, bias=sh.views["b1"], out=ws.h1, two_cta=c.two_cta,
@@ -493,16 +585,24 @@ class FusedDMoE(nn.Module):
         c.timer.mark("bwd_gate+dispatch_grad")
         tg, go, G = ws.tile_group, ws.group_off, c.G_tot
         gr = sh.grads
+        if c.small:
+            self._backward_small(epoch)
+            c.timer.mark("expert_ffn_bwd(dgrad+ln+fused wgrad/AMSGrad)")
+            dx = torch.empty(B, cfg.hidden, dtype=torch.bfloat16, device=gy.device)
+            K.combine_rows(c.dxd_off, idx, pair_row, None, dx, k, c.E_loc, flags_off=c.flags_off, slot=K.SLOT_DINPUT,
+                           epoch=epoch, signal=c.world > 1, wait=c.world > 1, status=c.status, route_owner=ws.route_owner)
+            c.timer.mark("bwd_combine")
+            return dx, dlogits
         K.grouped_colsum(c.gyd, tg, out=gr["b3"])
-        gemm.grouped_wgrad(c.gyd, ws.a2, go, G, out=gr["w3"], two_cta=c.two_cta)
+        gemm.grouped_wgrad(c.gyd, ws.a2, go, G, out=gr["w3"], two_cta=c.two_cta, accumulate=cfg.accumulate)
         gemm.grouped_linear(c.gyd, sh.bf16["w3"], tile_group=tg, w_is_kn=True, out=c.da, two_cta=c.two_cta)
         K.ln_relu_bwd(c.da, ws.h2, ws.mean2, ws.rstd2, sh.views["g2"], sh.views["be2"], tg, dh=c.dh, dgamma=gr["g2"],
                       dbeta=gr["be2"], dbias=gr["b2"])
-        gemm.grouped_wgrad(c.dh, ws.a1, go, G, out=gr["w2"], two_cta=c.two_cta)
+        gemm.grouped_wgrad(c.dh, ws.a1, go, G, out=gr["w2"], two_cta=c.two_cta, accumulate=cfg.accumulate)
         gemm.grouped_linear(c.dh, sh.bf16["w2"], tile_group=tg, w_is_kn=True, out=c.da, two_cta=c.two_cta)
         K.ln_relu_bwd(c.da, ws.h1, ws.mean1, ws.rstd1, sh.views["g1"], sh.views["be1"], tg, dh=c.dh, dgamma=gr["g1"],
                       dbeta=gr["be1"], dbias=gr["b1"])
-        gemm.grouped_wgrad(c.dh, ws.xd, go, G, out=gr["w1"], two_cta=c.two_cta)
+        gemm.grouped_wgrad(c.dh, ws.xd, go, G, out=gr["w1"], two_cta=c.two_cta, accumulate=cfg.accumulate)
         gemm.grouped_linear(c.dh, sh.bf16["w1"], tile_group=tg, w_is_kn=True, residual=c.gyd, out=c.dxd,
                             two_cta=c.two_cta)
         c.timer.mark("expert_ffn_bwd(wgrad+dgrad+ln)")
@@ -517,12 +617,55 @@ class FusedDMoE(nn.Module):
         c.timer.mark("bwd_combine")
         return dx, dlogits
 
+    def _backward_small(self, epoch):
+        """expert backward of the weight-streaming regime.  Order matters: the dgrad of a Linear reads the OLD weights, so
+        it runs before the fused wgrad+AMSGrad kernel of the same matrix updates them in place (reference: the optimizer
+        step follows the whole backward, lib/runtime/expert_backend.py:85-90)."""
+        c, ws, sh, cfg = self.ctx, self.ws, self.shard, self.cfg
+        tg, go, rows, T = ws.tile_group, ws.group_off, ws.group_rows, c.tile_rows
+        gr = sh.grads
+        opt = dict(lr=cfg.lr, betas=cfg.betas, eps=cfg.eps, amsgrad=cfg.amsgrad)
+
+        def wgrad(name, dy, x):   # dW never reaches HBM: TMEM accumulator -> AMSGrad epilogue -> TMA stores of p / m / v / vmax
+            K.wgrad_adam(dy, x, go, rows, p=sh.views[name][:self.E_loc], m=sh.m_views[name][:self.E_loc],
+                         v=sh.v_views[name][:self.E_loc], vmax=sh.vmax_views[name][:self.E_loc] if cfg.amsgrad else None,
+                         p_bf16=sh.bf16[name], step=sh.step, **opt)
+
+        K.bump_steps(sh.step, ws.step_rows)
+        K.grouped_colsum(c.gyd, tg, out=gr["b3"], tile_rows=T)
+        K.swapab_linear(c.gyd, sh.bf16["w3"], go, rows, out=c.da, w_is_kn=True)
+        wgrad("w3", c.gyd, ws.a2)
+        K.ln_relu_bwd(c.da, ws.h2, ws.mean2, ws.rstd2, sh.views["g2"], sh.views["be2"], tg, dh=c.dh, dgamma=gr["g2"],
+                      dbeta=gr["be2"], dbias=gr["b2"], tile_rows=T)
+        K.swapab_linear(c.dh, sh.bf16["w2"], go, rows, out=c.da, w_is_kn=True)
+        wgrad("w2", c.dh, ws.a1)
+        K.ln_relu_bwd(c.da, ws.h1, ws.mean1, ws.rstd1, sh.views["g1"], sh.views["be1"], tg, dh=c.dh, dgamma=gr["g1"],
+                      dbeta=gr["be1"], dbias=gr["b1"], tile_rows=T)
+        K.swapab_linear(c.dh, sh.bf16["w1"], go, rows, out=c.dxd, w_is_kn=True, residual=c.gyd)
+        wgrad("w1", c.dh, ws.xd)
+        # biases / LayerNorm affine: the ordinary fused AMSGrad restricted to the small segments
+        K.adam_step(sh.p, sh.g, sh.m, sh.v, sh.vmax, sh.p_bf16, sh.seg_sizes, sh.slots, step=sh.step,
+                    group_rows=ws.step_rows, zero_mask=SMALL_SEG_MASK, G_active=self.E_loc, seg_mask=SMALL_SEG_MASK, **opt)
+        sh.w8_dirty = True
+
     def apply_expert_gradients(self):
         sh, cfg, ws, c = self.shard, self.cfg, self.ws, self.ctx
-        K.bump_steps(sh.step, ws.step_rows)
+        rows, zero_mask = ws.step_rows, SMALL_SEG_MASK
+        if cfg.accumulate:
+            # asynchronous expert updates (dmoe_emulator.py:70-77): gradients accumulate in sh.g (wgrad accumulate=True) until
+            # the expert has seen >= update_every_inputs rows or >= update_every_steps steps since its first pending row
+            sh.pending_rows += ws.step_rows
+            sh.pending_steps += (sh.pending_rows > 0).to(torch.int32)
+            due = (sh.pending_rows > 0) & ((sh.pending_rows >= max(1, cfg.update_every_inputs)) |
+                                           (sh.pending_steps >= max(1, cfg.update_every_steps)))
+            sh.fire.copy_(due.to(torch.int32))
+            sh.pending_rows.mul_(1 - sh.fire)
+            sh.pending_steps.mul_(1 - sh.fire)
+            rows, zero_mask = sh.fire, (1 << len(SEG_NAMES)) - 1
+        K.bump_steps(sh.step, rows)
         K.adam_step(sh.p, sh.g, sh.m, sh.v, sh.vmax, sh.p_bf16, sh.seg_sizes, sh.slots, step=sh.step,
-                    group_rows=ws.step_rows, lr=cfg.lr, betas=cfg.betas, eps=cfg.eps, amsgrad=cfg.amsgrad,
-                    zero_mask=SMALL_SEG_MASK, G_active=self.E_loc, world=c.world,
+                    group_rows=rows, lr=cfg.lr, betas=cfg.betas, eps=cfg.eps, amsgrad=cfg.amsgrad,
+                    zero_mask=zero_mask, G_active=self.E_loc, world=c.world,
                     peer_bases=c.heap.peer_bases if c.S else None, shadow_of=ws.owned_shadow if c.S else None,
                     shadow_g_off=sh.g_off, me=c.rank)
         sh.w8_dirty = True

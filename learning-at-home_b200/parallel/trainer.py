@@ -37,10 +37,15 @@ class PendingLoss:
 
 class DMoETrainer:
     def __init__(self, cfg: DMoEConfig, group=None, device: Optional[torch.device] = None, profile_stages: bool = False,
-                 metrics_path: Optional[str] = None):
+                 metrics_path: Optional[str] = None, use_graph: Optional[bool] = None):
         """
         :param profile_stages: time every stage of a step with CUDA events (+ NVTX ranges); see ``last_stage_ms``
         :param metrics_path: append one JSON record per ``log_step()`` call to this file (structured step metrics)
+        :param use_graph: capture the WHOLE training step (forward, loss, backward, expert and trainer optimizers, the peer
+            flag protocol) in one CUDA graph after two eager steps and replay it afterwards.  Everything that changes from
+            step to step (flag epochs, failure-injection stream, Adam step counters) lives in device memory, so the replayed
+            graph is exact.  None = automatic: on for the small-batch (weight-streaming) regime where a step is ~130 short
+            kernels, off for the saturated regime where launch latency is hidden anyway.
         """
         from .profiler import MetricsLog
         self.cfg = cfg
@@ -60,8 +65,12 @@ class DMoETrainer:
         self.model = DMoEClassifier(cfg, self.ctx, device=self.device).to(self.device)
         self._flatten_trainer_params()
         self.step_count = 0
+        self.use_graph = bool(self.cuda and (self.ctx.small if use_graph is None else use_graph))
+        self._graph, self._graph_B, self._eager_steps = None, -1, 0
         B = cfg.tokens_per_rank
         if self.cuda:
+            self.step_dev = torch.zeros(1, dtype=torch.int32, device=self.device)   # trainer AMSGrad step count (device side)
+            self._one = torch.ones(1, dtype=torch.int32, device=self.device)
             # double-buffered staging: the NEXT step's inputs can cross PCIe on a copy stream while this step computes
             self._x_dev = [torch.empty(B, cfg.in_features, device=self.device) for _ in range(2)]
             self._y_dev = [torch.empty(B, dtype=torch.int64, device=self.device) for _ in range(2)]
@@ -116,20 +125,20 @@ class DMoETrainer:
         cfg = self.cfg
         self.step_count += 1
         if not self.cuda:
-            # CPU path: same maths through torch
-            if not hasattr(self, "_cpu_opt"):
-                self._cpu_opt = torch.optim.Adam([self.flat_p.requires_grad_(False)], lr=cfg.lr, betas=cfg.betas,
-                                                 eps=cfg.eps, amsgrad=cfg.amsgrad)
-            self.flat_p.grad = self.flat_g
-            self._cpu_opt.step()
-            self.flat_g.zero_()
+            # CPU path: the same flat AMSGrad maths as csrc/adam.cu on the SAME state buffers (flat_m / flat_v / flat_vmax),
+            # so checkpoints taken on CPU carry the optimizer state
+            with torch.no_grad():
+                K.adam_step_ref(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.flat_vmax, [self._n_pad], 1,
+                                step=torch.tensor([self.step_count]), lr=cfg.lr, betas=cfg.betas, eps=cfg.eps,
+                                amsgrad=cfg.amsgrad, zero_mask=1)
             return
         c = self.ctx
+        K.bump_steps(self.step_dev, self._one)
         if c.world > 1:
             epoch = c.next_epoch()
             K.signal_wait(c.flags_off, K.SLOT_TRAINER, epoch, c.status, signal=True, wait=True)
             K.adam_step(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.flat_vmax, None, [self._n_pad], 1,
-                        step_scalar=self.step_count, lr=cfg.lr, betas=cfg.betas, eps=cfg.eps, amsgrad=cfg.amsgrad,
+                        step=self.step_dev, lr=cfg.lr, betas=cfg.betas, eps=cfg.eps, amsgrad=cfg.amsgrad,
                         world=c.world, peer_grad_off=self.flat_g_off, peer_bases=c.heap.peer_bases,
                         grad_scale=1.0 / c.world)
             # nobody may overwrite its gradient buffer before every peer has consumed it
@@ -137,14 +146,48 @@ class DMoETrainer:
             self.flat_g.zero_()
         else:
             K.adam_step(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.flat_vmax, None, [self._n_pad], 1,
-                        step_scalar=self.step_count, lr=cfg.lr, betas=cfg.betas, eps=cfg.eps, amsgrad=cfg.amsgrad,
+                        step=self.step_dev, lr=cfg.lr, betas=cfg.betas, eps=cfg.eps, amsgrad=cfg.amsgrad,
                         zero_mask=1)
 
     # ------------------------------------------------------------------ steps
     def train_step_device(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
-        """one optimisation step on device tensors; returns the (device) loss tensor, no host synchronisation"""
+        """one optimisation step on device tensors; returns the (device) loss tensor, no host synchronisation.  With
+        ``use_graph`` the third and later calls replay ONE captured CUDA graph of the whole step."""
+        if not (self.use_graph and not self.ctx.timer.enabled):
+            return self._step_eager(x, y)
+        B = x.shape[0]
+        if self._graph is None or self._graph_B != B:
+            if self._eager_steps < 2:   # lazy initialisation (function attributes, cuBLAS workspaces, autograd threads)
+                self._eager_steps += 1
+                return self._step_eager(x, y)
+            self._capture(B)
+        self._gx.copy_(x, non_blocking=True)
+        self._gy.copy_(y, non_blocking=True)
+        self._graph.replay()
+        self.step_count += 1
+        native.count_launch(self._graph_launches)
+        return self._gloss
+
+    def _capture(self, B: int):
+        """capture one whole training step (fixed batch B) into a CUDA graph; nothing is executed here"""
+        cfg = self.cfg
+        self._gx = torch.zeros(B, cfg.in_features, device=self.device)
+        self._gy = torch.zeros(B, dtype=torch.int64, device=self.device)
+        torch.cuda.synchronize(self.device)
+        before, count_before = native.launches(), self.step_count
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._gloss = self._step_eager(self._gx, self._gy)
+        self._graph_launches = native.launches() - before   # our kernels per replay (bench: gpu_launches)
+        native.count_launch(-self._graph_launches)           # capture launched nothing
+        self.step_count = count_before
+        self._graph_B = B
+
+    def _step_eager(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
         self.model.train()
         timer = self.ctx.timer if self.cuda else None
+        if self.cuda:
+            self.ctx.begin_step()
         if timer is not None:
             timer.start()
         logits = self.model(x)
@@ -256,6 +299,8 @@ class DMoETrainer:
         """loss / accuracy of one batch.  COLLECTIVE on multi-GPU runs: the experts are sharded over the ranks, so every
         rank must call it at the same point (with its own batch of at most ``tokens_per_rank`` rows)."""
         self.model.eval()
+        if self.cuda:
+            self.ctx.begin_step()
         logits = self.model(x.to(self.device))
         y = y.to(self.device)
         return dict(loss=float(F.cross_entropy(logits.float(), y)), acc=float((logits.argmax(-1) == y).float().mean()))
@@ -271,10 +316,14 @@ class DMoETrainer:
                 uid = f"layer{li}." + expert_uid(self.cfg, block.first_expert + le)
                 experts[uid] = dict(model=block.shard.expert_state_dict(le),
                                     optimizer=block.shard.expert_optimizer_state(le))
+        if self.cuda:
+            torch.cuda.synchronize(self.device)
         trainer = dict(model={k: v.detach().clone().cpu() for k, v in self.model.state_dict().items()},
-                       exp_avg=self.flat_m.cpu(), exp_avg_sq=self.flat_v.cpu(), max_exp_avg_sq=self.flat_vmax.cpu(),
-                       step=self.step_count)
-        return dict(trainer=trainer, experts=experts, rng=torch.get_rng_state())
+                       exp_avg=self.flat_m.detach().clone().cpu(), exp_avg_sq=self.flat_v.detach().clone().cpu(),
+                       max_exp_avg_sq=self.flat_vmax.detach().clone().cpu(), step=self.step_count)
+        # the failure-injection stream position: device-side token base on GPU runs (csrc/moe.cu Peers::step_ctr)
+        token_base = int(self.ctx.step_ctr[2:4].view(torch.int64).item()) if self.cuda else 0
+        return dict(trainer=trainer, experts=experts, rng=torch.get_rng_state(), token_base=token_base)
 
     def load_state_dict(self, state):
         from .engine import expert_uid
@@ -285,6 +334,9 @@ class DMoETrainer:
             self.flat_v.copy_(state["trainer"]["exp_avg_sq"])
             self.flat_vmax.copy_(state["trainer"]["max_exp_avg_sq"])
         self.step_count = int(state["trainer"]["step"])
+        if self.cuda:
+            self.step_dev.fill_(self.step_count)
+            self.ctx.step_ctr[2:4].view(torch.int64).fill_(int(state.get("token_base", 0)))
         for li, block in enumerate(self.model.blocks):
             for le in range(block.E_loc):
                 uid = f"layer{li}." + expert_uid(self.cfg, block.first_expert + le)

@@ -143,13 +143,21 @@ def test_cpu_trainer_learns_and_checkpoint_roundtrip():
     assert losses[-1] < 0.5 * losses[0]
     assert int(trainer.model.blocks[0].shard.step.max()) == 25
     state = trainer.state_dict()
-    assert set(state) == {"trainer", "experts", "rng"} and "layer1.expert.1.0" in state["experts"]
+    assert set(state) == {"trainer", "experts", "rng", "token_base"} and "layer1.expert.1.0" in state["experts"]
+    assert float(state["trainer"]["exp_avg"].abs().sum()) > 0   # CPU checkpoints carry the trainer optimizer state
     assert "expert.layers.4.bias" in state["experts"]["layer0.expert.0.1"]["model"]
     clone = DMoETrainer(cfg)
     clone.load_state_dict(state)
     ev1, ev2 = trainer.evaluate(x, y), clone.evaluate(x, y)
     assert abs(ev1["loss"] - ev2["loss"]) < 1e-6 and clone.step_count == 25
     assert abs(trainer.train_step(x, y) - clone.train_step(x, y)) < 1e-5
+    # resumed run == continued run for several more steps (optimizer state restored, not just the weights)
+    for _ in range(3):
+        assert abs(trainer.train_step(x, y) - clone.train_step(x, y)) < 1e-5
+    # the returned state is a copy, not an alias of live buffers
+    before = state["trainer"]["exp_avg"].clone()
+    trainer.train_step(x, y)
+    assert torch.equal(before, state["trainer"]["exp_avg"])
 
 
 def test_failure_injection_on_oracle_path():

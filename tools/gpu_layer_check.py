@@ -145,10 +145,15 @@ def check_layer_fp8():
     check_layer(expert_dtype="fp8")
 
 
-def check_layer(expert_dtype="bf16"):
+def check_layer_small():
+    """same layer through the weight-streaming kernels (swap-AB GEMMs, fused wgrad + AMSGrad; csrc/small_m.cu)"""
+    check_layer(expert_path="small")
+
+
+def check_layer(expert_dtype="bf16", expert_path="big"):
     torch.manual_seed(3)
     cfg = E.DMoEConfig(hidden=512, grid_size=(4, 4), k=4, num_layers=1, tokens_per_rank=512, lr=1e-3,
-                       expert_dtype=expert_dtype)
+                       expert_dtype=expert_dtype, expert_path=expert_path)
     ctx = E.EngineContext(cfg)
     layer = E.FusedDMoE(cfg, ctx).cuda()
     B = 512
@@ -191,17 +196,25 @@ def check_layer(expert_dtype="bf16"):
         before = torch.stack([layer.shard.expert_state_dict(e)["expert." + E.REF_KEYS[n]] for e in range(16)]).cuda()
         perr[n] = (before - ref).abs().mean().item()
     errs["param_mean_abs_diff_after_step"] = max(perr.values())
+    # VALUE of the weight gradients: after the first AMSGrad step exp_avg = (1 - beta1) * grad
+    werr = {}
+    for n, li in (("w1", 0), ("w2", 3), ("w3", 6)):
+        ref = torch.stack([experts[e].layers[li].weight.grad if experts[e].layers[li].weight.grad is not None
+                           else torch.zeros_like(experts[e].layers[li].weight) for e in range(16)])
+        werr[n] = rel(layer.shard.m_views[n][:16] / (1 - cfg.betas[0]), ref)
+    errs["wgrad_rel_err"] = max(werr.values())
     # first Adam step moves every parameter by ~lr*sign(grad): a mean |diff| << lr means the gradients agree in sign
     tol = 1.0 if expert_dtype == "bf16" else 3.0
     ok = errs["y"] < 2e-2 * tol and errs["dx"] < 3e-2 * tol and errs["dproj"] < 5e-2 * tol and \
-        errs["param_mean_abs_diff_after_step"] < 1e-4 * tol
-    record("layer_16experts" + ("" if expert_dtype == "bf16" else "_" + expert_dtype), ok=bool(ok), **errs, per_param=perr,
-           steps=layer.shard.step.tolist())
+        errs["param_mean_abs_diff_after_step"] < 1e-4 * tol and errs["wgrad_rel_err"] < 3e-2 * tol
+    record("layer_16experts" + ("" if expert_dtype == "bf16" else "_" + expert_dtype) + ("" if expert_path == "big" else "_" + expert_path),
+           ok=bool(ok), **errs, per_param=perr, wgrad=werr, steps=layer.shard.step.tolist())
+    ctx.close()
 
 
 def main():
     print("device:", torch.cuda.get_device_name(0), flush=True)
-    for fn in (check_gate, check_ln, check_adam, check_layer, check_layer_fp8):
+    for fn in (check_gate, check_ln, check_adam, check_layer, check_layer_small, check_layer_fp8):
         try:
             fn()
         except Exception as e:  # noqa
