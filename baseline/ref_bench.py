@@ -40,9 +40,16 @@ def build_reference_trainer(hidden=512, num_experts=64, num_active=4, num_layers
     model = nn.Sequential(nn.Linear(in_features, hidden), *(make() for _ in range(num_layers)),
                           nn.LayerNorm(hidden), nn.Linear(hidden, num_classes)).to(device)
     opt = Optimizer(non_expert(model))
+    # same synthetic MNIST-shaped learnable task as the other arm (bench.py synthetic_mnist; duplicated here so that this
+    # harness imports nothing of the product)
+    gen = torch.Generator().manual_seed(4242)
+    protos = torch.randn(num_classes, in_features, generator=gen)
     gen = torch.Generator().manual_seed(seed)
-    xs_host = [torch.randn(batch_size, in_features, generator=gen).pin_memory() for _ in range(4)]
-    ys_host = [torch.randint(0, num_classes, (batch_size,), generator=gen).pin_memory() for _ in range(4)]
+    xs_host, ys_host = [], []
+    for _ in range(4):
+        yb = torch.randint(0, num_classes, (batch_size,), generator=gen)
+        xs_host.append((protos[yb] + 3.0 * torch.randn(batch_size, in_features, generator=gen)).pin_memory())
+        ys_host.append(yb.pin_memory())
     xs_dev = [x.to(device) for x in xs_host]
     ys_dev = [y.to(device) for y in ys_host]
     loss_host = torch.empty(1).pin_memory()

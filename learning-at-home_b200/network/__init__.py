@@ -17,6 +17,20 @@ from concurrent.futures import Future
 from typing import Dict, List, Optional, Sequence, Tuple
 
 from ..utils import PickleSerializer
+import io
+import pickle
+
+
+class _PlainUnpickler(pickle.Unpickler):
+    """DHT values come from arbitrary peers: accept the reference's pickled ((host, port), timestamp) / timestamp records
+    (tuples, strings, numbers need no globals) and refuse every pickle that names a class or function"""
+
+    def find_class(self, module, name):
+        raise pickle.UnpicklingError(f"DHT values may not reference {module}.{name}")
+
+
+def _loads_value(raw: bytes):
+    return _PlainUnpickler(io.BytesIO(raw)).load()
 from .dht import DHTNode
 
 UID_DELIMETER = "."
@@ -89,7 +103,7 @@ class TesseractNetwork:
         for uid, raw in zip(uids, found):
             expert = None
             if raw is not None:
-                (host, port), timestamp = PickleSerializer.loads(raw)
+                (host, port), timestamp = _loads_value(raw)
                 if (now - timestamp).total_seconds() <= heartbeat_expiration:
                     expert = RemoteExpert(uid=uid, host=host, port=port)
             experts.append(expert)
@@ -133,7 +147,7 @@ class TesseractNetwork:
         for i, prefix in enumerate(prefixes):
             raw = await lookups.pop(i)
             if raw is not None:
-                timestamp = PickleSerializer.loads(raw)
+                timestamp = _loads_value(raw)
                 if (datetime.datetime.now() - timestamp).total_seconds() <= heartbeat_expiration:
                     active.append(prefix)
                     if len(active) >= k:

@@ -5,13 +5,16 @@ The reference depends on the third-party ``kademlia`` package (/root/reference/l
 neither vendored nor installable offline; this is an independent implementation of the protocol surface the library
 needs (``listen``, ``bootstrap``, ``get``, ``set``): 160-bit SHA-1 ids, XOR metric, k-buckets (k=20, native C++ routing
 table in csrc/host_runtime.cpp), iterative lookups with alpha=3, RPCs PING / STORE / FIND_NODE / FIND_VALUE.
-Values carry a store timestamp; the newest one wins.  Messages are pickled dicts in single UDP datagrams.
+Values carry a store timestamp; the newest one wins.  Messages are msgpack maps in single UDP datagrams — a
+NON-EXECUTABLE encoding: a datagram from any host on the network is parsed, never unpickled (stored VALUES stay opaque
+bytes; what they contain is the business of the layer above).  Every field of an incoming message is type- and
+length-checked before it reaches the routing table (the native table copies exactly 20 id bytes).
 """
 import asyncio
 import ctypes
 import hashlib
 import os
-import pickle
+import msgpack
 import socket
 import struct
 import threading
@@ -24,6 +27,52 @@ K_BUCKET = 20
 ALPHA = 3
 RPC_TIMEOUT = 1.0
 VALUE_TTL = 3600.0
+
+
+MAX_VALUE_BYTES = 60000   # one UDP datagram
+
+
+def _is_id(x) -> bool:
+    return isinstance(x, bytes) and len(x) == 20
+
+
+def _valid_message(msg: dict) -> bool:
+    """types / lengths of every field of an incoming RPC (untrusted input)"""
+    if msg.get("t") not in ("q", "r") or not isinstance(msg.get("id"), bytes) or len(msg["id"]) != 8:
+        return False
+    if not _is_id(msg.get("sender")):
+        return False
+    for field in ("key", "target"):
+        if field in msg and not _is_id(msg[field]):
+            return False
+    if "value" in msg and not isinstance(msg["value"], bytes):
+        return False
+    if "ts" in msg and not isinstance(msg["ts"], (int, float)):
+        return False
+    if msg["t"] == "q":
+        m = msg.get("m")
+        if m not in ("ping", "store", "find_node", "find_value"):
+            return False
+        if m == "store" and not ("key" in msg and "value" in msg and "ts" in msg):
+            return False
+        if m == "find_node" and "target" not in msg:
+            return False
+        if m == "find_value" and "key" not in msg:
+            return False
+    if "nodes" in msg:
+        nodes = msg["nodes"]
+        if not isinstance(nodes, list):
+            return False
+        for entry in nodes:
+            if not (isinstance(entry, list) and len(entry) == 2 and _is_id(entry[0]) and isinstance(entry[1], list)
+                    and len(entry[1]) == 2 and isinstance(entry[1][0], str) and isinstance(entry[1][1], int)
+                    and 0 < entry[1][1] < 65536):
+                return False
+            try:
+                socket.inet_aton(entry[1][0])
+            except OSError:
+                return False
+    return True
 
 
 def sha1(data) -> bytes:
@@ -54,7 +103,7 @@ class RoutingTable:
         self._py: Dict[bytes, Tuple[str, int, float]] = {}
 
     def add(self, node_id: bytes, addr: Tuple[str, int]) -> bool:
-        if node_id == self.node_id:
+        if not _is_id(node_id) or node_id == self.node_id:
             return False
         if self._handle is not None:
             evict_id = ctypes.create_string_buffer(20)
@@ -72,6 +121,8 @@ class RoutingTable:
             self._py.pop(node_id, None)
 
     def closest(self, target: bytes, n: int = K_BUCKET) -> List[Tuple[bytes, Tuple[str, int]]]:
+        if not _is_id(target):
+            raise ValueError("routing-table targets are 20-byte ids")
         if self._handle is not None:
             ids = ctypes.create_string_buffer(20 * n)
             ips, ports = (ctypes.c_uint32 * n)(), (ctypes.c_uint16 * n)()
@@ -99,10 +150,16 @@ class _Protocol(asyncio.DatagramProtocol):
 
     def datagram_received(self, data, addr):
         try:
-            msg = pickle.loads(data)
+            msg = msgpack.unpackb(data, raw=False, strict_map_key=True, max_bin_len=MAX_VALUE_BYTES, max_str_len=64,
+                                  max_array_len=4 * K_BUCKET, max_map_len=16)
         except Exception:
             return
-        self.node._on_message(msg, addr)
+        if not isinstance(msg, dict) or not _valid_message(msg):
+            return
+        try:
+            self.node._on_message(msg, addr)
+        except Exception:   # a malformed but well-typed message must not take the endpoint down
+            return
 
 
 class DHTNode:
@@ -127,7 +184,7 @@ class DHTNode:
             self._protocol.transport.close()
 
     def _send(self, msg: dict, addr):
-        self._protocol.transport.sendto(pickle.dumps(msg, protocol=pickle.HIGHEST_PROTOCOL), addr)
+        self._protocol.transport.sendto(msgpack.packb(msg, use_bin_type=True), addr)
 
     async def _rpc(self, addr, method: str, **payload) -> Optional[dict]:
         rpc_id = os.urandom(8)
@@ -143,7 +200,7 @@ class DHTNode:
 
     def _on_message(self, msg: dict, addr):
         sender = msg.get("sender")
-        if isinstance(sender, bytes) and len(sender) == 20:
+        if _is_id(sender):
             self.table.add(sender, (addr[0], addr[1]))
         if msg.get("t") == "r":
             future = self._pending.get(msg.get("id"))
@@ -157,13 +214,13 @@ class DHTNode:
         elif method == "store":
             self._store_local(msg["key"], msg["value"], msg["ts"])
         elif method == "find_node":
-            reply["nodes"] = self.table.closest(msg["target"], K_BUCKET)
+            reply["nodes"] = [[nid, [ip, port]] for nid, (ip, port) in self.table.closest(msg["target"], K_BUCKET)]
         elif method == "find_value":
             hit = self.storage.get(msg["key"])
             if hit is not None and time.time() - hit[1] <= VALUE_TTL:
                 reply["value"], reply["ts"] = hit
             else:
-                reply["nodes"] = self.table.closest(msg["key"], K_BUCKET)
+                reply["nodes"] = [[nid, [ip, port]] for nid, (ip, port) in self.table.closest(msg["key"], K_BUCKET)]
         else:
             return
         self._send(reply, addr)

@@ -21,7 +21,7 @@ from typing import Dict, Iterator, List, Optional, Tuple
 import torch
 
 from .expert_backend import ExpertBackend
-from .task_pool import TaskPool, TaskPoolBase
+from .task_pool import TaskPool, TaskPoolBase, BatchAssemblyError
 
 
 class TesseractRuntime:
@@ -58,15 +58,21 @@ class TesseractRuntime:
             pool = self._next_pool()
             if pool is None:
                 continue
-            if copy_stream is not None:
-                with torch.cuda.stream(copy_stream):
+            try:
+                if copy_stream is not None:
+                    with torch.cuda.stream(copy_stream):
+                        batch_index, batch = pool.load_batch_to_runtime(timeout, self.device)
+                        ready = torch.cuda.Event()
+                        ready.record(copy_stream)
+                    item = (pool, batch_index, batch, ready)
+                else:
                     batch_index, batch = pool.load_batch_to_runtime(timeout, self.device)
-                    ready = torch.cuda.Event()
-                    ready.record(copy_stream)
-                yield pool, batch_index, batch, ready
-            else:
-                batch_index, batch = pool.load_batch_to_runtime(timeout, self.device)
-                yield pool, batch_index, batch, None
+                    item = (pool, batch_index, batch, None)
+            except (BatchAssemblyError, TimeoutError) as e:
+                # per-batch failure (its tasks already carry the exception): remember it and keep serving the other pools
+                self.last_error = e
+                continue
+            yield item
 
     def _on_cuda(self) -> bool:
         return self.device is not None and torch.device(self.device).type == "cuda" and torch.cuda.is_available()

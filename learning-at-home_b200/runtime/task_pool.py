@@ -27,6 +27,10 @@ from ..utils import BatchTensorProto
 Task = namedtuple("Task", ("future", "args", "timestamp"))
 
 
+class BatchAssemblyError(RuntimeError):
+    """a formed batch could not be assembled; its tasks have already been failed (per-batch error, not fatal)"""
+
+
 class TaskPoolBase:
     """Common interface between pools and TesseractRuntime (the runtime only needs these members)."""
 
@@ -100,8 +104,35 @@ class TaskPool(TaskPoolBase):
         self._alive = False
 
     # ------------------------------------------------------------------ producer side (connection handlers)
+    def validate_task(self, args) -> None:
+        """reject a request that cannot be batched with the others BEFORE it enters the queue (a malformed request must
+        cost its author an 'err_' reply, not the server its runtime): argument count, tensor-ness, dtype, trailing shape
+        and equal row counts are checked against ``inputs_schema``"""
+        if len(args) != len(self.inputs_schema):
+            raise ValueError(f"expected {len(self.inputs_schema)} input tensors, got {len(args)}")
+        rows = None
+        for i, (arg, proto) in enumerate(zip(args, self.inputs_schema)):
+            if not isinstance(arg, torch.Tensor):
+                raise TypeError(f"input {i} is not a tensor")
+            want = tuple(proto.size[1:]) if getattr(proto, "size", None) is not None else None
+            if arg.dim() < 1 or (want is not None and tuple(arg.shape[1:]) != want):
+                raise ValueError(f"input {i} has shape {tuple(arg.shape)}, expected [batch, {', '.join(map(str, want or ()))}]")
+            if getattr(proto, "dtype", None) is not None and arg.dtype != proto.dtype:
+                raise TypeError(f"input {i} has dtype {arg.dtype}, expected {proto.dtype}")
+            if rows is None:
+                rows = arg.shape[0]
+            elif arg.shape[0] != rows:
+                raise ValueError("all inputs of a request must have the same number of rows")
+        if not rows:
+            raise ValueError("empty request")
+
     def submit_task(self, *args: torch.Tensor) -> Future:
         future = Future()
+        try:
+            self.validate_task(args)
+        except Exception as e:  # delivered to the author through the future (-> 'err_' reply)
+            future.set_exception(e)
+            return future
         task = Task(future, args, time.time())
         with self._lock:
             while self.pool_size and len(self._tasks) >= self.pool_size:
@@ -168,6 +199,13 @@ class TaskPool(TaskPoolBase):
         batch_index = self._next_batch_index
         self._next_batch_index += 1
         self._pending[batch_index] = tasks
+        try:
+            return batch_index, self._assemble(tasks, device)
+        except Exception as e:   # a batch that cannot be assembled fails ITS tasks only; the runtime keeps serving
+            self.fail_batch(batch_index, e)
+            raise BatchAssemblyError(str(e)) from e
+
+    def _assemble(self, tasks, device):
         rows = sum(map(self.get_task_size, tasks))
         to_cuda = device is not None and torch.device(device).type == "cuda"
         batch = []
@@ -191,7 +229,7 @@ class TaskPool(TaskPoolBase):
         if to_cuda:
             self._staging_free = torch.cuda.Event()
             self._staging_free.record(torch.cuda.current_stream(device))
-        return batch_index, batch
+        return batch
 
     def send_outputs_from_runtime(self, batch_index: int, batch_outputs: Sequence):
         """split the outputs of a processed batch by task and resolve the tasks' futures"""

@@ -103,6 +103,9 @@ def socket_loop(sock, experts, stop_event: Optional[threading.Event] = None):
             if stop_event is not None and stop_event.is_set():
                 break
             continue
+        except Exception as e:  # noqa: one bad connection must never cost the server an acceptor thread
+            print(f"[TesseractServer] connection handler error ignored: {type(e).__name__}: {e}", flush=True)
+            continue
 
 
 __all__ = ["TesseractServer", "TesseractRuntime", "ExpertBackend", "socket_loop", "handle_connection",

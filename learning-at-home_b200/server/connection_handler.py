@@ -21,8 +21,8 @@ def handle_connection(connection_tuple: Tuple[socket, str], experts: Dict[str, E
                 header = tensor_wire.REQUEST_HEADERS[header]
             else:
                 payload = PytorchSerializer.loads(connection.recv_raw())
-        except (RuntimeError, OSError, EOFError, ValueError):
-            return  # client went away / garbage
+        except Exception:  # noqa: client went away / garbage bytes (bad pickle, truncated frame, oversized length prefix, ...)
+            return      # drop the connection; the acceptor thread lives on
         try:
             if header == "fwd_":
                 uid, inputs = payload

@@ -71,15 +71,22 @@ class Connection(AbstractContextManager):
     def recv_header(self) -> str:
         return self._recv_exact(self.header_size).decode()
 
+    #: largest payload a peer may announce (the length prefix is attacker-controlled: never allocate it blindly)
+    max_payload = 1 << 32
+
+    def _recv_length(self) -> int:
+        length = int.from_bytes(self._recv_exact(self.payload_length_size), byteorder="big")
+        if length > self.max_payload:
+            raise ValueError(f"announced payload of {length} bytes exceeds the limit of {self.max_payload}")
+        return length
+
     def recv_raw(self, max_package: int = 0) -> bytes:
         """:param max_package: kept for API compatibility with the reference; ignored"""
-        length = int.from_bytes(self._recv_exact(self.payload_length_size), byteorder="big")
-        return bytes(self._recv_exact(length))
+        return bytes(self._recv_exact(self._recv_length()))
 
     def recv_buffer(self) -> bytearray:
         """payload as the receive buffer itself (no copy): for zero-copy decoders (utils/tensor_wire.py)"""
-        length = int.from_bytes(self._recv_exact(self.payload_length_size), byteorder="big")
-        return self._recv_exact(length)
+        return self._recv_exact(self._recv_length())
 
     def recv_message(self) -> Tuple[str, bytes]:
         return self.recv_header(), self.recv_raw()

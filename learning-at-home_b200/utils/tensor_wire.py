@@ -24,6 +24,7 @@ MAGIC = b"LAHT"
 _DTYPES = [torch.float32, torch.float64, torch.float16, torch.bfloat16, torch.int64, torch.int32, torch.int16, torch.int8,
            torch.uint8, torch.bool]
 _CODE = {dt: i for i, dt in enumerate(_DTYPES)}
+MAX_TENSORS, MAX_NDIM = 4096, 8
 REQUEST_HEADERS = {"fwdT": "fwd_", "bwdT": "bwd_"}
 REPLY_HEADER = "resT"
 
@@ -56,23 +57,45 @@ def encode(uid: str, tensors: Sequence[torch.Tensor]) -> Tuple[List[memoryview],
 def decode(buf) -> Tuple[str, Tuple[torch.Tensor, ...]]:
     """``buf``: bytes-like (kept alive by the returned tensors, which alias it)"""
     view = memoryview(buf)
+    total = view.nbytes
+
+    def need(off, n):   # every field is attacker-controlled: check it against the bytes actually received
+        if n < 0 or off + n > total:
+            raise ValueError("truncated or inconsistent tensor frame")
+
+    need(0, 6)
     if bytes(view[:4]) != MAGIC:
         raise ValueError("not a tensor frame")
     (uid_len,) = struct.unpack_from("<H", view, 4)
     off = 6
+    need(off, uid_len + 4)
     uid = bytes(view[off: off + uid_len]).decode()
     off += uid_len
     (n,) = struct.unpack_from("<I", view, off)
     off += 4
+    if n > MAX_TENSORS:
+        raise ValueError(f"frame announces {n} tensors (limit {MAX_TENSORS})")
     out = []
     for _ in range(n):
+        need(off, 2)
         code, ndim = struct.unpack_from("<BB", view, off)
         off += 2
+        if code >= len(_DTYPES) or ndim > MAX_NDIM:
+            raise ValueError("bad dtype code / rank in tensor frame")
+        need(off, 8 * ndim + 8)
         dims = struct.unpack_from(f"<{ndim}q", view, off)
         off += 8 * ndim
         (nbytes,) = struct.unpack_from("<Q", view, off)
         off += 8
         dtype = _DTYPES[code]
+        numel = 1
+        for d in dims:
+            if d < 0:
+                raise ValueError("negative dimension in tensor frame")
+            numel *= d
+        if numel * torch.empty((), dtype=dtype).element_size() != nbytes:   # dims must describe exactly the bytes sent
+            raise ValueError("tensor dims do not match its byte count")
+        need(off, nbytes)
         if nbytes:
             carrier = torch.int16 if dtype == torch.bfloat16 else torch.uint8 if dtype == torch.bool else dtype
             t = torch.frombuffer(view[off: off + nbytes], dtype=carrier)

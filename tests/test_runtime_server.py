@@ -205,3 +205,54 @@ def test_tensor_wire_roundtrip_and_protocol_negotiation(server):
     assert torch.allclose(y_fast, y_ref)
     y_fast.sum().backward()                                       # 'bwdT' works too (the server steps the expert)
     assert x.grad is not None and x.grad.shape == x.shape
+
+
+def test_malformed_requests_do_not_kill_the_server():
+    """a 'fwd_' with no tensors, mismatched shapes, garbage bytes, a truncated frame, a bad dtype code and an
+    absurd length prefix each cost their author an error (or the connection) — the single acceptor thread and the runtime
+    keep serving (the reference loses the expert's pool process / hangs its clients)."""
+    import socket as pysocket
+    import struct
+    from lah_b200.utils import Connection, PytorchSerializer, tensor_wire
+    experts = {"e": make_backend("e")}
+    srv = lib.TesseractServer(None, experts, port=0, conn_handler_processes=1)   # ONE acceptor: losing it = dead server
+    srv.run_in_background()
+    try:
+        def raw(payload: bytes):
+            with pysocket.create_connection(("127.0.0.1", srv.port), timeout=5) as s:
+                s.sendall(payload)
+                s.settimeout(2)
+                try:
+                    return s.recv(1 << 16)
+                except (pysocket.timeout, ConnectionResetError):
+                    return b""
+
+        def request(header, obj):
+            with Connection.create("127.0.0.1", srv.port) as c:
+                c.send_raw(header, PytorchSerializer.dumps(obj))
+                return c.recv_message()
+
+        h, _ = request("fwd_", ("e", ()))                                    # no tensors at all
+        assert h == "err_"
+        h, _ = request("fwd_", ("e", (torch.randn(2, 5),)))                  # wrong trailing shape
+        assert h == "err_"
+        h, _ = request("fwd_", ("e", (torch.randn(2, 16).double(),)))        # wrong dtype
+        assert h == "err_"
+        h, _ = request("bwd_", ("e", (torch.randn(2, 16), torch.randn(3, 16))))   # row counts disagree
+        assert h == "err_"
+        raw(b"fwd_" + (7).to_bytes(8, "big") + b"garbage")                   # bad pickle
+        raw(b"fwdT" + (3).to_bytes(8, "big") + b"LAH")                       # truncated tensor frame
+        frame = tensor_wire.MAGIC + struct.pack("<H", 1) + b"e" + struct.pack("<I", 1) + struct.pack("<BBqQ", 200, 1, 4, 16) + b"0" * 16
+        raw(b"fwdT" + len(frame).to_bytes(8, "big") + frame)                 # dtype code out of range
+        frame = tensor_wire.MAGIC + struct.pack("<H", 1) + b"e" + struct.pack("<I", 1) + struct.pack("<BBqQ", 0, 1, 1 << 40, 16) + b"0" * 16
+        raw(b"fwdT" + len(frame).to_bytes(8, "big") + frame)                 # dims claim 4 TiB, 16 bytes sent
+        raw(b"fwd_" + (1 << 62).to_bytes(8, "big"))                          # absurd length prefix
+        # still alive and correct
+        remote = lib.RemoteExpert("e", "127.0.0.1", srv.port)
+        x = torch.randn(3, 16)
+        assert torch.allclose(remote(x), experts["e"].expert(x), atol=1e-6)
+        assert all(t.is_alive() for t in srv._threads)
+    finally:
+        srv.shutdown()
+    with pytest.raises(ValueError):
+        tensor_wire.decode(bytearray(b"LAHT\x01\x00e\xff\xff\xff\xff"))      # 4e9 tensors announced
