@@ -43,6 +43,8 @@ def parse_args():
                     help="secondary measurement reported under 'saturated': samples per GPU per step in the compute-bound regime")
     ap.add_argument("--no-saturated", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-nccl-baseline", action="store_true",
+                    help="skip the in-run NCCL(all_to_all_single)+cuBLAS(bmm)+fused-Adam measurement of the same step")
     ap.add_argument("--extra-configs", action="store_true", help="also measure BASELINE configs 4 (4096 experts, fp8) and 5 (failure 0.1)")
     ap.add_argument("--expert-path", choices=["auto", "small", "big"], default="auto")
     ap.add_argument("--hidden", type=int, default=512)
@@ -194,6 +196,13 @@ def run_ours(args):
         return
     out = _measure_ours(args, rank, world, local_rank, args.batch_per_gpu, path=args.expert_path, tag="named")
     extras = {}
+    if not args.no_nccl_baseline:
+        try:
+            nb = measure_nccl_baseline(args, rank, world, local_rank, args.batch_per_gpu, steps=max(10, args.steps))
+            extras["nccl_baseline"] = nb
+            extras["vs_nccl_baseline"] = (out["value"] / nb["value"]) if out else None
+        except Exception as e:
+            extras["nccl_baseline"] = {"error": f"{type(e).__name__}: {e}"[:300]}
     if not args.no_parity:
         try:
             extras["parity"] = parity_check(rank, world)
@@ -415,6 +424,9 @@ def parity_check(rank, world):
         layer = E.FusedDMoE(cfg, ctx).cuda()
         torch.manual_seed(0)
         oracle = E.FusedDMoE(cfg, None, device=torch.device("cuda")).cuda()   # all experts local, plain PyTorch fp32
+        # fp32 maths, but activations / GEMM operands rounded to bf16 exactly where the engine stores bf16: without it ~0.4 % of
+        # the ReLU gates differ between an fp32 and a bf16 forward, which alone is ~5 % rel-L2 on the weight gradients
+        oracle.ref_emulate_bf16 = True
         gen = torch.Generator().manual_seed(7)
         x_all = torch.randn(world * B, 512, generator=gen).to(torch.bfloat16)
         g_all = torch.randn(world * B, 512, generator=gen).to(torch.bfloat16)
@@ -447,7 +459,7 @@ def parity_check(rank, world):
         e = dict(zip(("y", "dx", "dproj", "w1", "wgrad_w2"), [float(v) for v in t]))
         e["steps_equal"] = bool(mn.item() == 1.0)
         e["shadowed_experts"] = shadowed
-        e["ok"] = bool(e["y"] < 2e-2 and e["dx"] < 3e-2 and e["dproj"] < 5e-2 and e["w1"] < 1e-4 and e["wgrad_w2"] < 3e-2
+        e["ok"] = bool(e["y"] < 1e-2 and e["dx"] < 2e-2 and e["dproj"] < 3e-2 and e["w1"] < 1e-4 and e["wgrad_w2"] < 2e-2
                        and e["steps_equal"] and (name == "small" or world == 1 or shadowed > 0))
         out[name] = e
         torch.cuda.synchronize()
@@ -457,57 +469,67 @@ def parity_check(rank, world):
         del layer, oracle, ctx
         torch.cuda.empty_cache()
     out["ok"] = all(v["ok"] for v in out.values())
-    out["what"] = "1 DMoE layer fwd+bwd+AMSGrad on all ranks vs dense fp32 oracle; rel-L2 errors (w1: mean |diff| after the step), max over ranks"
+    out["what"] = "1 DMoE layer fwd+bwd+AMSGrad on all ranks vs dense PyTorch oracle (fp32 maths, bf16-rounded activations); rel-L2 errors (w1: mean |diff| after the step), max over ranks"
     return out
 
 
 # ------------------------------------------------------------------------------------------------ NCCL + cuBLAS baseline
-def run_baseline(args):
-    """same model / step through parallel/baseline.py: product-key gate, index_select permute, all_to_all_single (NCCL),
-    per-expert F.linear under bf16 autocast (cuBLAS), one torch Adam(amsgrad) per expert"""
-    rank, world, local_rank = dist_setup(args.gpus)
-    cuda = torch.cuda.is_available()
-    if not cuda and not os.environ.get("LAH_BENCH_ALLOW_CPU"):
-        print(json.dumps({"impl": "baseline", "unavailable": "no CUDA device visible"}))
-        return
+def measure_nccl_baseline(args, rank, world, local_rank, B, steps=None, warmup=3):
+    """the same step through parallel/baseline_fast.py: same gate, fixed-capacity buffers, all_to_all_single (NCCL, equal
+    splits), cuBLAS bmm under bf16 autocast, fused torch Adam(amsgrad) — no host synchronisation inside a step"""
+    import gc
     import lah_b200  # noqa
     from lah_b200.parallel.engine import DMoEConfig
-    from lah_b200.parallel.baseline import BaselineTrainer
-    B = args.batch_per_gpu
-    grid = tuple(args.grid) if len(args.grid) > 1 else (8, 8) if args.grid == [64] else tuple(args.grid)
-    cfg = DMoEConfig(hidden=args.hidden, grid_size=grid, k=args.k, num_layers=args.layers, tokens_per_rank=B,
-                     failure_rate=args.failure_rate, gate_mode="product_key")
-    trainer = BaselineTrainer(cfg, dtype=torch.bfloat16 if cuda else torch.float32)
-    gen = torch.Generator().manual_seed(1234 + rank)
-    dev = trainer.device
-    xs = [torch.randn(B, cfg.in_features, generator=gen).to(dev) for _ in range(2)]
-    ys = [torch.randint(0, cfg.num_classes, (B,), generator=gen).to(dev) for _ in range(2)]
+    from lah_b200.parallel.baseline_fast import FastBaselineTrainer
+    steps = max(10, steps or args.steps)
+    cfg = DMoEConfig(hidden=args.hidden, grid_size=tuple(args.grid), k=args.k, num_layers=args.layers, tokens_per_rank=B,
+                     gate_mode=args.gate)
+    trainer = FastBaselineTrainer(cfg)
+    xs_host, ys_host = synthetic_mnist(B, 4, seed=1234 + rank, in_features=cfg.in_features)
+    xs = [x.cuda() for x in xs_host]
+    ys = [y.cuda() for y in ys_host]
+    losses = []
 
     def step(i):
-        trainer.train_step_device(xs[i % 2], ys[i % 2])
+        losses.append(trainer.train_step_device(xs[i % 4], ys[i % 4]).reshape(1))
 
-    for i in range(args.warmup):
+    barrier_sync(world)
+    for i in range(max(3, warmup)):
         step(i)
-    if cuda:
-        sampler = ClockSampler(local_rank)
-        sampler.start()
-        ms = timed(step, args.steps, world)
-        clocks = sampler.stop()
-    else:  # CPU smoke path of this arm (tests)
-        t0 = time.time()
-        for i in range(args.steps):
-            step(i)
-        ms, clocks = (time.time() - t0) * 1e3, {}
-    value = B * world * args.steps / (ms / 1e3)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms = timed(step, steps, world)
+    clocks = sampler.stop()
+    curve = [float(t) for t in torch.cat(losses).cpu()]
+    value = B * world * steps / (ms / 1e3)
+    out = {"impl": "baseline (torch.topk + NCCL all_to_all_single + cuBLAS bmm + fused torch Adam; parallel/baseline_fast.py)",
+           "value": value, "unit": "samples/s", "ms_per_step": ms / steps, "steps": steps, "warmup": max(3, warmup),
+           "capacity_rows_per_expert_and_rank": trainer.capacity, "clocks": clocks,
+           "loss_first_last": [curve[0], curve[-1]], "global_batch": B * world}
+    del trainer, xs, ys
+    gc.collect()
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_baseline(args):
+    rank, world, local_rank = dist_setup(args.gpus)
+    if not torch.cuda.is_available():
+        print(json.dumps({"impl": "baseline", "unavailable": "no CUDA device visible"}))
+        return
+    r = measure_nccl_baseline(args, rank, world, local_rank, args.batch_per_gpu)
     if rank == 0:
+        E = int(torch.tensor(args.grid).prod())
         print(json.dumps({
             "metric": "DMoE training samples/sec (whole job, device-timed, max over ranks)", "impl": "baseline",
-            "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": value / 16.8,
-            "dtype": "bf16 autocast" if cuda else "fp32", "data": DATA_STR,
-            "config": {"model": f"same model through torch.topk + all_to_all_single + cuBLAS + torch Adam; grid {grid}",
-                       "global_batch": B * world, "seq_len": 1, "parallelism": f"ep{world}+dp{world} (NCCL all_to_all_single)"},
-            "clocks": clocks, "gpu_launches": 0}))
+            "value": r["value"], "unit": "samples/s", "n_gpus": world, "steps": r["steps"], "warmup": r["warmup"],
+            "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": r["value"] / 16.8,
+            "dtype": "bf16 autocast", "data": DATA_STR,
+            "config": {"model": MODEL_STR.format(h=args.hidden, L=args.layers, E=E, k=args.k), "implementation": r["impl"],
+                       "global_batch": r["global_batch"], "batch_per_gpu": args.batch_per_gpu, "seq_len": 1,
+                       "parallelism": f"ep{world}+dp{world} (NCCL all_to_all_single)",
+                       "capacity_rows_per_expert_and_rank": r["capacity_rows_per_expert_and_rank"]},
+            "clocks": r["clocks"], "gpu_launches": 0, "loss_first_last": r["loss_first_last"]}))
     if world > 1:
         import torch.distributed as dist
         dist.barrier()

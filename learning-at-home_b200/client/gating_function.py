@@ -62,6 +62,9 @@ class GatingFunction(nn.Module):
         assert input.dim() == 2
         fused = getattr(self.network, "fused_layer", None)
         if fused is not None and input.is_cuda and not args and not kwargs:
+            # in-box fast path (InBoxNetwork.bind_engine): liveness comes from the device-resident heartbeat table, the whole
+            # layer runs in the sm_100a kernels; k_min / timeout_after_k_min map to DMoEConfig.peer_timeout_ms
+            self.network.sync_alive(force=False)
             return fused.forward_with_gate(input, self.proj)
 
         grid_scores = self.proj(input).split_with_sizes(self.grid_size, dim=-1)

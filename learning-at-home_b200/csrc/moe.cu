@@ -36,7 +36,31 @@ struct Peers {
     //   the gate's token_offset (failure-injection RNG stream).  Bumped by step_begin_kernel.  nullptr -> 0.
     int* step_ctr;
     int spin_timeout_ms;          // flag-wait timeout (0 -> ~10 s); a timed-out wait raises STATUS_TIMEOUT and goes on
+    // NVSwitch multicast alias of the symmetric heap (same offsets; nullptr when the arena is a legacy IPC mapping): one
+    // multimem.st reaches every rank's copy, multimem.ld_reduce returns the in-switch sum of all copies (NVLS)
+    char* mc_base;
 };
+
+__device__ __forceinline__ void multimem_st_release_u32(void* mc_addr, int v) {
+    asm volatile("multimem.st.release.sys.global.u32 [%0], %1;" ::"l"(mc_addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void multimem_st_u32(void* mc_addr, int v) {
+    asm volatile("multimem.st.relaxed.sys.global.u32 [%0], %1;" ::"l"(mc_addr), "r"(v) : "memory");
+}
+
+// publish `epoch` into flag word [slot][me] of EVERY rank.  Call from the threads [0, world) of one warp after the data
+// stores (each caller fences).  With a multicast mapping this is ONE store replicated by the switch.
+__device__ __forceinline__ void signal_all_ranks(const Peers& peers, long long flags_off, int slot, int epoch, int tid) {
+    if (peers.mc_base) {
+        if (tid == 0) {
+            __threadfence_system();
+            multimem_st_release_u32(peers.mc_base + flags_off + (static_cast<long long>(slot) * MAX_WORLD + peers.me) * 4, epoch);
+        }
+    } else if (tid < peers.world) {
+        __threadfence_system();
+        st_release_sys(reinterpret_cast<int*>(peers.base[tid] + flags_off) + slot * MAX_WORLD + peers.me, epoch);
+    }
+}
 
 __device__ __forceinline__ int epoch_of(const Peers& peers, int rel) {
     return rel + (peers.step_ctr ? *reinterpret_cast<volatile const int*>(peers.step_ctr) : 0);
@@ -254,16 +278,21 @@ __global__ void __launch_bounds__(1024) layout_exchange_kernel(Peers peers, Layo
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int me = peers.me, world = peers.world;
     a.epoch = epoch_of(peers, a.epoch);
-    // 1. publish my counts to every peer (plain P2P stores), then release the epoch flag on every peer
-    for (int r = 0; r < world; ++r) {
-        int* dst = reinterpret_cast<int*>(peers.base[r] + a.cnt_all_off) + static_cast<long long>(me) * a.E;
-        for (int e = tid; e < a.E; e += blockDim.x) dst[e] = a.counts[e];
+    // 1. publish my counts to every peer (one multimem.st per word through the switch, or plain P2P stores), then
+    //    release the epoch flag on every peer
+    if (peers.mc_base) {
+        int* dst = reinterpret_cast<int*>(peers.mc_base + a.cnt_all_off) + static_cast<long long>(me) * a.E;
+        for (int e = tid; e < a.E; e += blockDim.x) multimem_st_u32(dst + e, a.counts[e]);
+    } else {
+        for (int r = 0; r < world; ++r) {
+            int* dst = reinterpret_cast<int*>(peers.base[r] + a.cnt_all_off) + static_cast<long long>(me) * a.E;
+            for (int e = tid; e < a.E; e += blockDim.x) dst[e] = a.counts[e];
+        }
     }
+    __threadfence_system();
     __syncthreads();
+    signal_all_ranks(peers, a.flags_off, a.slot, a.epoch, tid);
     if (tid < world) {
-        __threadfence_system();
-        int* f = reinterpret_cast<int*>(peers.base[tid] + a.flags_off) + a.slot * MAX_WORLD + me;
-        st_release_sys(f, a.epoch);
         // 2. wait for everybody's counts
         const int* fw = reinterpret_cast<const int*>(peers.base[me] + a.flags_off) + a.slot * MAX_WORLD + tid;
         const unsigned long long t0 = globaltimer_ns();
@@ -554,9 +583,13 @@ __global__ void __launch_bounds__(256) scatter_rows_kernel(Peers peers, ScatterA
             *a.done_counter = 0;
             __threadfence_system();
             const int epoch = epoch_of(peers, a.epoch);
-            for (int r = 0; r < peers.world; ++r) {
-                int* f = reinterpret_cast<int*>(peers.base[r] + a.flags_off) + a.slot * MAX_WORLD + peers.me;
-                st_release_sys(f, epoch);
+            if (peers.mc_base) {
+                multimem_st_release_u32(peers.mc_base + a.flags_off + (static_cast<long long>(a.slot) * MAX_WORLD + peers.me) * 4, epoch);
+            } else {
+                for (int r = 0; r < peers.world; ++r) {
+                    int* f = reinterpret_cast<int*>(peers.base[r] + a.flags_off) + a.slot * MAX_WORLD + peers.me;
+                    st_release_sys(f, epoch);
+                }
             }
         }
     }
@@ -569,17 +602,58 @@ __global__ void signal_wait_kernel(Peers peers, long long flags_off, int slot, i
                                    int* status) {
     const int lane = threadIdx.x;
     epoch = epoch_of(peers, epoch);
-    if (do_signal && lane < peers.world) {
-        __threadfence_system();
-        int* f = reinterpret_cast<int*>(peers.base[lane] + flags_off) + slot * MAX_WORLD + peers.me;
-        st_release_sys(f, epoch);
-    }
+    if (do_signal) signal_all_ranks(peers, flags_off, slot, epoch, lane);
     if (do_wait && lane < peers.world) {
         const int* f = reinterpret_cast<const int*>(peers.base[peers.me] + flags_off) + slot * MAX_WORLD + lane;
         const unsigned long long t0 = globaltimer_ns();
         spin_until_ge(f, epoch, status, peers.spin_timeout_ms);
         account_wait(peers, t0, peers.world);
     }
+}
+
+// NVLS all-reduce (in place, one shot) of a float buffer that lives at the same offset of every rank's symmetric heap:
+// rank r owns the r-th slice: multimem.ld_reduce returns the sum of all ranks' copies (added INSIDE the switch), the
+// scaled result goes back to every rank with one multimem.st.  Every rank therefore ends up with the bit-identical
+// reduced gradient (replicated trainer parameters must not drift apart), and each element crosses NVLink once per
+// direction instead of `world` P2P loads per rank.  Callers bracket it with flag barriers (all gradients written /
+// all slices reduced).  Reference: the trainers of the emulator share these parameters under a lock (notebook cell 3).
+__global__ void __launch_bounds__(256) nvls_allreduce_kernel(Peers peers, long long off, long long n, float scale) {
+    const long long per = ((n / 4 + peers.world - 1) / peers.world) * 4;   // float4 granularity
+    const long long lo = per * peers.me, hi = min(n, lo + per);
+    float* mc = reinterpret_cast<float*>(peers.mc_base + off);
+    for (long long i = lo + (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4; i < hi;
+         i += static_cast<long long>(gridDim.x) * blockDim.x * 4) {
+        float4 r;
+        asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                     : "l"(mc + i)
+                     : "memory");
+        r.x *= scale; r.y *= scale; r.z *= scale; r.w *= scale;
+        asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc + i), "f"(r.x), "f"(r.y),
+                     "f"(r.z), "f"(r.w)
+                     : "memory");
+    }
+}
+
+// liveness broadcast: the owner of experts [first, first + count) stamps their heartbeat (ms, 64 bit) into the table of
+// EVERY rank with one multimem.st per expert (declare_experts of the reference: one DHT store per uid and prefix,
+// /root/reference/lib/network/__init__.py:69-86); without multicast: unicast P2P stores
+__global__ void heartbeat_kernel(Peers peers, long long hb_off, int first, int count, long long now_ms) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    if (peers.mc_base) {
+        asm volatile("multimem.st.relaxed.sys.global.u64 [%0], %1;" ::"l"(reinterpret_cast<long long*>(peers.mc_base + hb_off) + first + i),
+                     "l"(now_ms)
+                     : "memory");
+    } else {
+        for (int r = 0; r < peers.world; ++r) reinterpret_cast<long long*>(peers.base[r] + hb_off)[first + i] = now_ms;
+    }
+}
+
+// alive[e] = (now - hb[e] <= max_age) for every expert: turns the heartbeat table into the mask the gate kernel reads
+__global__ void alive_from_heartbeats_kernel(const long long* hb, unsigned char* alive, int E, long long now_ms, long long max_age_ms) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < E) alive[e] = (hb[e] > 0 && now_ms - hb[e] <= max_age_ms) ? 1 : 0;
 }
 
 // one thread: advance the device-side step counters (see Peers::step_ctr)
@@ -609,11 +683,9 @@ template <int VEC_PER_LANE>
 __global__ void __launch_bounds__(256) combine_rows_kernel(Peers peers, CombineArgs a) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (a.do_signal || a.do_wait) a.epoch = epoch_of(peers, a.epoch);
-    if (a.do_signal && blockIdx.x == 0 && threadIdx.x < peers.world) {
+    if (a.do_signal && blockIdx.x == 0 && threadIdx.x < 32) {
         // everything launched before this kernel on the stream (the last expert GEMM) is complete: tell the peers
-        __threadfence_system();
-        int* f = reinterpret_cast<int*>(peers.base[threadIdx.x] + a.flags_off) + a.slot * MAX_WORLD + peers.me;
-        st_release_sys(f, a.epoch);
+        signal_all_ranks(peers, a.flags_off, a.slot, a.epoch, threadIdx.x);
     }
     if (a.do_wait) {
         if (threadIdx.x < peers.world) {
@@ -815,9 +887,17 @@ int lah_set_peers(const unsigned long long* bases, int world, int me) {
     g_peers.wait_ns = nullptr;
     g_peers.step_ctr = nullptr;
     g_peers.spin_timeout_ms = 0;
+    g_peers.mc_base = nullptr;
     g_peers_set = true;
     return 0;
 }
+
+// multicast alias of the symmetric heap (0 = none): enables the multimem.* paths
+int lah_set_multicast(unsigned long long mc_base) {
+    g_peers.mc_base = reinterpret_cast<char*>(mc_base);
+    return 0;
+}
+unsigned long long lah_get_multicast() { return reinterpret_cast<unsigned long long>(g_peers.mc_base); }
 
 // device-side step counters: int32[4] (see Peers::step_ctr); NULL disables (epochs / token offsets are then absolute)
 int lah_set_step_counters(int* step_ctr) {
@@ -830,6 +910,30 @@ const int* lah_get_epoch_base() { return g_peers.step_ctr; }
 int lah_set_spin_timeout_ms(int ms) {
     g_peers.spin_timeout_ms = ms;
     return 0;
+}
+
+int lah_nvls_allreduce(long long off, long long n, float scale, cudaStream_t st) {
+    if (!g_peers_set || !g_peers.mc_base) return -10;
+    if (n % 4 || off % 16) return -2;
+    long long blocks = (n / 4 / g_peers.world + 255) / 256;
+    if (blocks < 1) blocks = 1;
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    nvls_allreduce_kernel<<<(int)blocks, 256, 0, st>>>(g_peers, off, n, scale);
+    return -(int)cudaGetLastError();
+}
+
+int lah_heartbeat(long long hb_off, int first, int count, long long now_ms, cudaStream_t st) {
+    if (!g_peers_set) return -10;
+    if (count <= 0) return 0;
+    heartbeat_kernel<<<(count + 127) / 128, 128, 0, st>>>(g_peers, hb_off, first, count, now_ms);
+    return -(int)cudaGetLastError();
+}
+
+int lah_alive_from_heartbeats(const long long* hb, unsigned char* alive, int E, long long now_ms, long long max_age_ms,
+                              cudaStream_t st) {
+    if (E <= 0) return 0;
+    alive_from_heartbeats_kernel<<<(E + 255) / 256, 256, 0, st>>>(hb, alive, E, now_ms, max_age_ms);
+    return -(int)cudaGetLastError();
 }
 
 int lah_step_begin(int epoch_delta, long long token_delta, cudaStream_t st) {

@@ -245,12 +245,16 @@ swapab_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const __g
                 mbar_wait(&tmem_full[as], aphase);
                 tcgen05_fence_after();
                 const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_group * 32) << 16) + as * BN_MAX;
+                // the padding rows of the group's last 16-row block are WRITTEN too (their inputs are zero rows, so they get
+                // bias / zero): every later kernel may then read whole 16-row blocks without meeting stale memory, and the
+                // k-step masked wgrad sees exact zeros there
+                const int n16 = (nn + 15) & ~15;
 #pragma unroll 1
-                for (int c0 = 0; c0 < nn; c0 += 32) {
+                for (int c0 = 0; c0 < n16; c0 += 32) {
                     uint32_t r[32];
                     tmem_ld_32x32(taddr + c0, r);
                     tmem_ld_wait();
-                    const int cn = min(32, nn - c0);
+                    const int cn = min(32, n16 - c0);
                     const long long row0 = off + n0 + c0;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {

@@ -30,6 +30,61 @@ class InBoxNetwork:
         self._endpoints: Dict[str, Tuple[str, int]] = {}
         self._lock = threading.Lock()
         self._alive = bool(start)
+        self.fused_layer = None      # set by bind_engine(): GatingFunction then runs the sm_100a layer for CUDA inputs
+        self._engine = None          # (ctx, cfg) of the bound in-box engine
+        self._last_sync = 0.0
+        self._ages_cache = (0.0, None)
+
+    # ------------------------------------------------------------------ in-box engine binding
+    def bind_engine(self, layer, sync_period: float = 1.0):
+        """Attach a ``lah_b200.parallel.engine.FusedDMoE`` layer (or a ``DMoETrainer`` -> its first DMoE layer).
+
+        * ``lib.GatingFunction(network=this, ...)`` called on a CUDA tensor then runs the fused layer (product-key gate with
+          the GatingFunction's own ``proj``, P2P dispatch, tcgen05 expert FFN, combine; backward + expert AMSGrad);
+        * ``declare_experts`` of uids that belong to the engine's grid and live on THIS rank stamps their heartbeat into the
+          device-resident table of EVERY rank (multimem.st over NVSwitch), and the gate kernel's liveness mask is refreshed
+          from that table at most every ``sync_period`` seconds — heartbeats reach the kernel without a host-side table;
+        * ``get_experts`` / ``first_k_active`` answer for the experts of ALL ranks from the same table."""
+        layer = getattr(layer, "model", layer)
+        layer = layer.blocks[0] if hasattr(layer, "blocks") else layer
+        assert getattr(layer, "ctx", None) is not None, "bind_engine needs a GPU FusedDMoE layer (EngineContext)"
+        self.fused_layer, self._engine, self._sync_period = layer, (layer.ctx, layer.cfg), sync_period
+        return self
+
+    def _engine_index(self, uid: str) -> Optional[int]:
+        """global expert id of ``uid`` in the bound engine's grid, or None"""
+        if self._engine is None:
+            return None
+        _, cfg = self._engine
+        parts = uid.split(self.UID_DELIMETER)
+        nd = len(cfg.grid_size)
+        if len(parts) != nd + 1 or self.UID_DELIMETER.join(parts[:-nd]) != cfg.uid_prefix:
+            return None
+        try:
+            coords = [int(p) for p in parts[-nd:]]
+        except ValueError:
+            return None
+        e = 0
+        for c, size in zip(coords, cfg.grid_size):
+            if not 0 <= c < size:
+                return None
+            e = e * size + c
+        return e
+
+    def sync_alive(self, heartbeat_expiration=HEARTBEAT_EXPIRATION, force: bool = True):
+        """refresh the gate kernel's liveness mask from the device-resident heartbeat table (rate limited unless forced)"""
+        if self._engine is None:
+            return
+        now = time.time()
+        if force or now - self._last_sync >= self._sync_period:
+            self._engine[0].refresh_alive(heartbeat_expiration, now)
+            self._last_sync = now
+
+    def _engine_age(self, e: int) -> float:
+        now = time.time()
+        if self._ages_cache[1] is None or now - self._ages_cache[0] > 0.2:
+            self._ages_cache = (now, self._engine[0].heartbeat_ages(now))
+        return float(self._ages_cache[1][e]) + (now - self._ages_cache[0])
 
     # process-like API of TesseractNetwork
     def start(self):
@@ -76,6 +131,18 @@ class InBoxNetwork:
     # ------------------------------------------------------------------ TesseractNetwork API
     def declare_experts(self, uids: Sequence[str], addr, port, wait_timeout=0, owner: int = 0, slots=None):
         now = time.time()
+        if self._engine is not None:   # heartbeats of engine experts hosted here go to the device table of every rank
+            ctx = self._engine[0]
+            mine = sorted(e for e in (self._engine_index(uid) for uid in uids)
+                          if e is not None and e // ctx.E_loc == ctx.rank)
+            start = 0
+            while start < len(mine):   # contiguous runs -> one launch each
+                end = start
+                while end + 1 < len(mine) and mine[end + 1] == mine[end] + 1:
+                    end += 1
+                ctx.heartbeat((mine[start], end - start + 1), now)
+                start = end + 1
+            self._ages_cache = (0.0, None)
         for i, uid in enumerate(uids):
             self._put("expert", uid, owner, slots[i] if slots is not None else i, now)
             with self._lock:
@@ -89,6 +156,10 @@ class InBoxNetwork:
         out = []
         for uid in uids:
             hit = self._fresh("expert", uid, heartbeat_expiration)
+            if hit is None and self._engine is not None:   # an expert of another rank: device-resident table
+                e = self._engine_index(uid)
+                if e is not None and self._engine_age(e) <= heartbeat_expiration:
+                    hit = (e // self._engine[0].E_loc, e % self._engine[0].E_loc)
             if hit is None:
                 out.append(None)
             else:

@@ -31,6 +31,10 @@ def _lib():
         "lah_ln_relu_bwd_t": [P, P, P, P, P, P, P, P, P, P, P, I, I, I, I, P],
         "lah_grouped_colsum_t": [P, L, P, I, P, I, I, P],
         "lah_set_step_counters": [P],
+        "lah_set_multicast": [c_ull],
+        "lah_nvls_allreduce": [L, L, Fl, P],
+        "lah_heartbeat": [L, I, I, L, P],
+        "lah_alive_from_heartbeats": [P, P, I, L, L, P],
         "lah_set_spin_timeout_ms": [I],
         "lah_step_begin": [I, L, P],
         "lah_swapab_linear": [P, L, I, P, I, I, I, I, P, L, P, P, P, P, L, P, I, I, P, P, I, P],
@@ -121,6 +125,30 @@ def set_peers(bases, me):
 def set_wait_counter(counter):
     """int64 device tensor [1] accumulating the ns this rank spends blocked on peer flags (None disables)"""
     native.check(_lib().lah_set_wait_counter(ptr(counter)), "lah_set_wait_counter")
+
+
+def set_multicast(mc_base):
+    """multicast (NVLS) alias of the symmetric heap, 0 = none; enables the multimem.* paths of csrc/moe.cu"""
+    native.check(_lib().lah_set_multicast(int(mc_base)), "lah_set_multicast")
+
+
+def nvls_allreduce(off, n, scale=1.0):
+    """in-place one-shot NVLS all-reduce of the fp32 buffer at symmetric-heap offset ``off`` (multimem.ld_reduce + multimem.st);
+    bracket with flag barriers"""
+    native.check(_lib().lah_nvls_allreduce(int(off), int(n), float(scale), stream_ptr()), "lah_nvls_allreduce")
+    native.count_launch()
+
+
+def heartbeat(hb_off, first, count, now_ms):
+    """stamp the heartbeat of experts [first, first+count) into EVERY rank's table (multimem.st / P2P stores)"""
+    native.check(_lib().lah_heartbeat(int(hb_off), int(first), int(count), int(now_ms), stream_ptr()), "lah_heartbeat")
+    native.count_launch()
+
+
+def alive_from_heartbeats(hb, alive, now_ms, max_age_ms):
+    native.check(_lib().lah_alive_from_heartbeats(ptr(hb), ptr(alive), alive.numel(), int(now_ms), int(max_age_ms),
+                                                  stream_ptr()), "lah_alive_from_heartbeats")
+    native.count_launch()
 
 
 def set_step_counters(ctr):

@@ -182,6 +182,12 @@ class EngineContext:
         K.set_spin_timeout_ms(cfg.peer_timeout_ms)
         assert 2 * cfg.num_layers + 4 < self.EPOCH_STRIDE
         self.alive = torch.ones(self.E, dtype=torch.uint8, device=self.device)
+        # device-resident expert index shared by ALL ranks ("DHT collapse"): hb[e] = last heartbeat (ms) of expert
+        # e, stamped into every rank's copy by its owner (multimem.st through NVSwitch / P2P stores); refresh_alive() turns
+        # it into the liveness mask the gate kernel reads.  All ones until heartbeats are used.
+        self.hb, self.hb_off = self.heap.alloc((self.E,), torch.int64)
+        self.hb.zero_()
+        self._hb_stream = None
         self.epoch = 0
         self.token_counter = 0
         from .profiler import StageTimer
@@ -202,6 +208,37 @@ class EngineContext:
         K.set_wait_counter(None)
         K.set_step_counters(None)
         self.heap.close()
+
+    # ------------------------------------------------------------------ liveness (heartbeat -> device table -> gate kernel)
+    def heartbeat(self, experts=None, now: Optional[float] = None):
+        """declare my experts alive on EVERY rank (reference: NetworkHandlerThread -> declare_experts,
+        /root/reference/lib/server/network_handler.py:17-20).  ``experts``: (first, count) range of GLOBAL expert ids hosted
+        here, default all of mine.  Runs on a side stream so that a heartbeat thread never interleaves with a step."""
+        import time
+        first, count = experts if experts is not None else (self.rank * self.E_loc, self.E_loc)
+        now_ms = int((time.time() if now is None else now) * 1000)
+        if self._hb_stream is None:
+            self._hb_stream = torch.cuda.Stream(self.device)
+        with torch.cuda.stream(self._hb_stream):
+            K.heartbeat(self.hb_off, first, count, now_ms)
+
+    def refresh_alive(self, heartbeat_expiration: float = 120.0, now: Optional[float] = None):
+        """alive[e] = heartbeat of e is younger than ``heartbeat_expiration`` seconds (on the device, no host copy)"""
+        import time
+        now_ms = int((time.time() if now is None else now) * 1000)
+        if self._hb_stream is None:
+            self._hb_stream = torch.cuda.Stream(self.device)
+        with torch.cuda.stream(self._hb_stream):
+            K.alive_from_heartbeats(self.hb, self.alive, now_ms, int(heartbeat_expiration * 1000))
+
+    def heartbeat_ages(self, now: Optional[float] = None) -> torch.Tensor:
+        """seconds since the last heartbeat of every expert (inf = never declared); synchronises"""
+        import time
+        if self._hb_stream is not None:
+            self._hb_stream.synchronize()
+        hb = self.hb.cpu().double()
+        now_ms = (time.time() if now is None else now) * 1000
+        return torch.where(hb > 0, (now_ms - hb) / 1000.0, torch.full_like(hb, float("inf")))
 
     def begin_step(self):
         """advance the device-side epoch / token bases (one tiny kernel) and restart the step-relative counters; called at
@@ -464,6 +501,7 @@ class FusedDMoE(nn.Module):
             self.ws = None
         self.shard = ExpertShard(cfg, self.E_loc, self.first_expert, dev, layer_index, ctx=ctx)
         self.ref_fail_mask = None  # tests can inject an explicit failure mask into the oracle path
+        self.ref_emulate_bf16 = False   # oracle path: round activations / weights to bf16 where the GPU path stores bf16
         self._ref_rows = None
         self._ref_leaves = {}   # CPU mode: local expert -> {segment: leaf view} of the experts used since the last update
 
@@ -487,7 +525,7 @@ class FusedDMoE(nn.Module):
         assert x.dim() == 2 and x.shape[1] == self.cfg.hidden
         logits = self.gate_logits(x, proj)
         if self.ctx is None:
-            return self._forward_ref(x, logits)
+            return self._forward_ref(x, logits, emulate_bf16=self.ref_emulate_bf16)
         assert x.shape[0] <= self.cfg.tokens_per_rank, "batch exceeds DMoEConfig.tokens_per_rank"
         return _FusedDMoEFunction.apply(x.to(torch.bfloat16).contiguous(), logits.contiguous(), self)
 

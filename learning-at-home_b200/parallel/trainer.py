@@ -134,7 +134,16 @@ class DMoETrainer:
             return
         c = self.ctx
         K.bump_steps(self.step_dev, self._one)
-        if c.world > 1:
+        if c.world > 1 and c.heap.mc_base:
+            # NVLS: gradients complete everywhere -> in-switch all-reduce (multimem.ld_reduce + multimem.st, every rank gets the
+            # bit-identical mean) -> all slices written -> plain local AMSGrad that also zeroes the gradient buffer
+            epoch = c.next_epoch()
+            K.signal_wait(c.flags_off, K.SLOT_TRAINER, epoch, c.status, signal=True, wait=True)
+            K.nvls_allreduce(self.flat_g_off, self._n_pad, 1.0 / c.world)
+            K.signal_wait(c.flags_off, K.SLOT_BARRIER, epoch, c.status, signal=True, wait=True)
+            K.adam_step(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.flat_vmax, None, [self._n_pad], 1,
+                        step=self.step_dev, lr=cfg.lr, betas=cfg.betas, eps=cfg.eps, amsgrad=cfg.amsgrad, zero_mask=1)
+        elif c.world > 1:
             epoch = c.next_epoch()
             K.signal_wait(c.flags_off, K.SLOT_TRAINER, epoch, c.status, signal=True, wait=True)
             K.adam_step(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.flat_vmax, None, [self._n_pad], 1,

@@ -26,9 +26,14 @@ from ..utils import BatchTensorProto, DUMMY_BATCH_SIZE, nested_compare, nested_f
 class ExpertBackend(nn.Module):
     def __init__(self, name: str, expert: nn.Module, opt: torch.optim.Optimizer, *,
                  args_schema: Tuple[BatchTensorProto, ...] = None, kwargs_schema: Dict[str, BatchTensorProto] = None,
-                 outputs_schema: Union[BatchTensorProto, Tuple[BatchTensorProto, ...]] = None, **kwargs):
+                 outputs_schema: Union[BatchTensorProto, Tuple[BatchTensorProto, ...]] = None, native: bool = True,
+                 **kwargs):
+        """:param native: run FeedforwardBlock experts that live on a CUDA device through the sm_100a kernels
+        (runtime/native_executor.py: swap-AB tcgen05 GEMMs, fused LayerNorm, fused weight-gradient + AMSGrad) instead of
+        eager PyTorch; anything the executor does not support falls back to the module itself"""
         super().__init__()
         self.expert, self.opt, self.name = expert, opt, name
+        self.native, self._executor, self._executor_key = native, None, None
         self.args_schema = args_schema = tuple(args_schema or ())
         self.kwargs_schema = kwargs_schema = dict(kwargs_schema or {})
         assert args_schema or kwargs_schema, ("expert must receive at least one positional or keyword input. "
@@ -52,13 +57,34 @@ class ExpertBackend(nn.Module):
         self.update_count = 0
 
     # ------------------------------------------------------------------ tasks
+    def native_executor(self, inputs):
+        """the sm_100a executor of this expert, or None (CPU tensors, unsupported expert / optimizer, no GPU)"""
+        if not self.native or len(inputs) < 1 or not inputs[0].is_cuda or self.kwargs_schema or len(self.args_schema) != 1:
+            return None
+        first = next(self.expert.parameters(), None)
+        key = (id(first), first.device if first is not None else None)
+        if self._executor_key != key:   # (re)build after .to(device) / load_checkpoint
+            from .native_executor import make_executor
+            self._executor, self._executor_key = make_executor(self.expert, self.opt), key
+            if self._executor is not None:
+                self._executor_key = (id(next(self.expert.parameters())), first.device)
+        return self._executor
+
     def forward(self, *inputs: torch.Tensor) -> Tuple[torch.Tensor, ...]:
+        executor = self.native_executor(inputs)
+        if executor is not None and inputs[0].dim() == 2:
+            return (executor.forward(inputs[0]),)
         args, kwargs = nested_pack(inputs, structure=self.forward_schema)
         with torch.no_grad():
             outputs = self.expert(*args, **kwargs)
         return tuple(nested_flatten(outputs))
 
     def backward(self, *inputs: torch.Tensor) -> Tuple[torch.Tensor, ...]:
+        executor = self.native_executor(inputs)
+        if executor is not None and len(inputs) == 2 and inputs[0].dim() == 2:
+            grad_x = executor.backward(inputs[0], inputs[1].to(inputs[0].device))   # dgrad + fused wgrad/AMSGrad: one update
+            self.update_count += 1
+            return (grad_x,)
         (args, kwargs), grad_outputs = nested_pack(inputs, structure=self.backward_schema)
         with torch.enable_grad():
             args = [t.detach().clone().requires_grad_(t.is_floating_point()) for t in args]
@@ -97,3 +123,5 @@ class ExpertBackend(nn.Module):
         self.load_state_dict(ckpt["model"])
         self.opt.load_state_dict(ckpt["optimizer"])
         self.update_count = int(ckpt.get("update_count", 0))
+        if self._executor is not None:   # the optimizer now owns fresh state tensors: re-bind them to the flat buffers
+            self._executor.bind()

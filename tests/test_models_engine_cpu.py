@@ -283,3 +283,16 @@ def test_dead_experts_are_never_routed_to():
     for before, block in zip(steps_before, trainer.model.blocks):
         delta = block.shard.step - before
         assert int(delta[4:8].sum()) == 0 and int(delta.sum()) > 0   # dead experts received no rows, hence no optimizer steps
+
+
+def test_fast_nccl_baseline_formulation_learns_on_cpu():
+    """parallel/baseline_fast.py (what `bench.py --impl baseline` measures): fixed-capacity dispatch without host syncs"""
+    from lah_b200.parallel.baseline_fast import FastBaselineTrainer
+    torch.manual_seed(0)
+    for gate in ("emulator", "product_key"):
+        cfg = E.DMoEConfig(hidden=32, grid_size=(4,) if gate == "emulator" else (2, 2), k=2, num_layers=2, in_features=12,
+                           tokens_per_rank=32, lr=3e-3, gate_mode=gate)
+        tr = FastBaselineTrainer(cfg, device=torch.device("cpu"))
+        x, y = torch.randn(32, 12), torch.randint(0, 10, (32,))
+        losses = [float(tr.train_step_device(x, y)) for _ in range(25)]
+        assert losses[-1] < 0.6 * losses[0], losses
