@@ -1,98 +1,60 @@
 """
-Multi-trainer client of the throughput experiment (CLI parity:
-/root/reference/experiments/throughput/throughput_client.py:18-85; same flags and the same metric definitions:
-latency = mean wall time per batch excluding the first; throughput = jobs * batch * (batches + 1) / wall).
+Multi-trainer client of the throughput experiment (CLI parity with /root/reference/experiments/throughput/
+throughput_client.py: same flags, same metrics — latency = mean wall time per batch without the first, throughput =
+jobs * batch * (batches + 1) / wall — and the same printed lines).
 
-Experts of different hosts are interleaved into one chain; after every layer the trainer sleeps ping * Weibull(1) to
-emulate network latency; `--jobs` concurrent trainers (threads here; the RPCs release the GIL) play the role of
-pipelining.  Forward only, like the reference.
+The chain visits the experts of all hosts interleaved (expert i of host 0, expert i of host 1, ..., expert i+1 of host 0,
+...), every hop is one blocking ``RemoteExpert`` call followed by the emulated lag sleep(ping * Weibull(1)); `--jobs`
+concurrent trainers keep the servers busy (threads: the socket I/O releases the GIL).  Forward only, like the reference.
 
     python -m lah_b200.experiments.throughput.throughput_client -j 64 --hosts 127.0.0.1:8080 127.0.0.1:8081 \
         --block-type ffn --layers-per-gpu 56
 """
 from argparse import ArgumentParser
-from concurrent.futures import ThreadPoolExecutor
-from functools import partial
-from itertools import chain
-from time import sleep, time
 
 import numpy as np
 import torch
-import torch.nn as nn
 
 from ... import RemoteExpert
-from ...models.layers import name_to_block, name_to_input
+from ...models.layers import name_to_input
+from .harness import Chain, Hop, LatencyModel, add_common_flags, meter_from_args, ping_grid
 
 
-class ExpertsWithLatency(nn.Module):
-    def __init__(self, experts):
-        super().__init__()
-        self.experts = nn.Sequential(*experts)
-
-    def forward(self, x, ping):
-        for layer in self.experts:
-            x = layer(x)
-            if ping:
-                sleep(ping * np.random.weibull(1))
-        return x
+def parse_host(address: str):
+    host, _, port = address.rpartition(":")
+    return host, int(port)
 
 
-@torch.no_grad()
-def measure_perf(ping, model, x, num_batches):
-    latencies = []
-    for _ in range(num_batches + 1):
-        start = time()
-        model(x, ping=ping)
-        latencies.append(time() - start)
-    return latencies[1:]
-
-
-def build_chain(hosts, layers_per_gpu):
-    per_host = []
-    for address in hosts:
-        host, port = address.split(":")
-        per_host.append([RemoteExpert(f"expert{i}", host=host, port=int(port)) for i in range(layers_per_gpu)])
-    return ExpertsWithLatency(list(chain.from_iterable(zip(*per_host))))  # interleave across hosts
+def build_chain(hosts, layers_per_gpu) -> Chain:
+    endpoints = [parse_host(a) for a in hosts]
+    hops = []
+    for layer in range(layers_per_gpu):          # interleave: consecutive hops always change host
+        for host, port in endpoints:
+            hops.append(Hop(RemoteExpert(f"expert{layer}", host=host, port=port)))
+    return Chain(hops)
 
 
 def run(args, printer=print):
     np.random.seed(0)
     torch.manual_seed(0)
-    model = build_chain(args.hosts, args.layers_per_gpu)
+    chain = build_chain(args.hosts, args.layers_per_gpu)
     x = name_to_input[args.block_type](args.batch_size, args.hid_dim).normal_()
-    measure = partial(measure_perf, model=model, x=x, num_batches=args.batches_for_throughput)
+    meter = meter_from_args(args)
     results = []
-    with ThreadPoolExecutor(args.jobs) as pool:
-        for ping in np.linspace(0, args.max_ping, args.linspace_points):
-            latencies = measure_perf(ping, model, x, args.batches_for_latency)
-            throughputs = []
-            for _ in range(args.throughput_runs):
-                start = time()
-                list(pool.map(measure, [ping] * args.jobs))
-                throughputs.append(args.jobs * args.batch_size * (args.batches_for_throughput + 1) / (time() - start))
-            row = dict(ping=float(ping), latency=float(np.mean(latencies)),
-                       latency_std=float(np.std(latencies, ddof=1)) if len(latencies) > 1 else 0.0,
-                       throughput=float(np.mean(throughputs)),
-                       throughput_std=float(np.std(throughputs, ddof=1)) if len(throughputs) > 1 else 0.0)
-            results.append(row)
-            printer(f"ModelParallel (ours, ping={ping:.2f}):\t{row['latency']:.2f}±{row['latency_std']:.2f}\t"
-                    f"{row['throughput']:.2f}±{row['throughput_std']:.2f}")
+    for ping in ping_grid(args):
+        lag = LatencyModel(ping) if ping else None
+        m = meter.measure(lambda: chain(x, latency=lag), concurrency=args.jobs, count_warm_batch=True)
+        row = dict(ping=ping, latency=m.latency, latency_std=m.latency_std, throughput=m.throughput,
+                   throughput_std=m.throughput_std)
+        results.append(row)
+        printer(m.line(f"ModelParallel (ours, ping={ping:.2f})"))
     return results
 
 
 def make_parser():
-    parser = ArgumentParser()
+    parser = add_common_flags(ArgumentParser(description=__doc__))
     parser.add_argument("-j", "--jobs", type=int, required=True)
     parser.add_argument("--hosts", nargs="+", required=True)
-    parser.add_argument("--hid-dim", type=int, default=1024)
-    parser.add_argument("--batches-for-latency", type=int, default=10)
-    parser.add_argument("--batches-for-throughput", type=int, default=100)
-    parser.add_argument("--throughput-runs", type=int, default=10)
-    parser.add_argument("--batch-size", type=int, default=2048)
-    parser.add_argument("--linspace-points", type=int, default=10)
-    parser.add_argument("--layers-per-gpu", type=int, default=56)
-    parser.add_argument("--block-type", choices=name_to_block.keys(), required=True)
-    parser.add_argument("--max-ping", type=float, default=0.2)
     return parser
 
 

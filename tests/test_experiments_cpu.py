@@ -60,3 +60,56 @@ def test_inbox_chain_schedule_invariants():
                     assert layer == (position[wave] + 1) % L      # the wave advanced by exactly one layer
                 position[wave] = layer
             assert waves == set(range(world))               # all waves in flight, one per rank
+
+
+def test_throughput_client_against_live_servers():
+    """throughput_client drives two TesseractServers (experts interleaved across hosts) and reports latency / throughput"""
+    import lah_b200 as lib
+    from lah_b200.models import FeedforwardBlock
+    from lah_b200.experiments.throughput import throughput_client as tc
+    servers = []
+    try:
+        for _ in range(2):
+            experts = {}
+            for i in range(2):
+                block = FeedforwardBlock(16)
+                experts[f"expert{i}"] = lib.ExpertBackend(name=f"expert{i}", expert=block, opt=torch.optim.Adam(block.parameters()),
+                                                          args_schema=(lib.BatchTensorProto(16),),
+                                                          outputs_schema=lib.BatchTensorProto(16), max_batch_size=64)
+            servers.append(lib.TesseractServer(None, experts, port=0, conn_handler_processes=4).run_in_background())
+        args = tc.make_parser().parse_args(["-j", "3", "--hosts", *[f"127.0.0.1:{s.port}" for s in servers], "--block-type", "ffn",
+                                            "--hid-dim", "16", "--batch-size", "4", "--layers-per-gpu", "2",
+                                            "--batches-for-latency", "2", "--batches-for-throughput", "2", "--throughput-runs", "2",
+                                            "--linspace-points", "2", "--max-ping", "0.001"])
+        chain = tc.build_chain(args.hosts, args.layers_per_gpu)
+        assert [(h.fn.uid, h.fn.port) for h in chain.hops] == [("expert0", servers[0].port), ("expert0", servers[1].port),
+                                                                ("expert1", servers[0].port), ("expert1", servers[1].port)]
+        rows = tc.run(args, printer=lambda *_: None)
+        assert len(rows) == 2 and all(r["throughput"] > 0 and r["latency"] > 0 for r in rows)
+        assert sum(s.runtime.samples_processed for s in servers) >= 2 * 4 * (1 + 2 + 2 * 3 * 3)
+    finally:
+        for s in servers:
+            s.shutdown()
+
+
+def test_rpc_throughput_baseline_two_processes():
+    """torch.distributed.rpc baseline: rank 0 drives a chain hosted by rank 1 (CPU tensors on the wire)"""
+    import os
+    import socket
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    code = ("import sys; sys.path.insert(0, %r); import lah_b200; from lah_b200.experiments.throughput import rpc_throughput as r; "
+            "out = r.run(r.make_parser().parse_args(sys.argv[1:])); print('RESULT', out)") % root
+    common = ["--world-size", "2", "--block-type", "ffn", "--hid-dim", "16", "--batch-size", "4", "--layers-per-gpu", "3",
+              "--batches-for-latency", "1", "--batches-for-throughput", "2", "--throughput-runs", "2"]
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), CUDA_VISIBLE_DEVICES="")
+    procs = [subprocess.Popen([sys.executable, "-c", code, "--rank", str(r), *common], env=env, stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in (0, 1)]
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    line = [l for l in outs[0].splitlines() if l.startswith("RESULT")][0]
+    assert "None" not in line and float(line.split("(")[1].split(",")[0]) > 0
