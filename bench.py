@@ -47,6 +47,7 @@ def parse_args():
                     help="skip the in-run NCCL(all_to_all_single)+cuBLAS(bmm)+fused-Adam measurement of the same step")
     ap.add_argument("--extra-configs", action="store_true", help="also measure BASELINE configs 4 (4096 experts, fp8) and 5 (failure 0.1)")
     ap.add_argument("--expert-path", choices=["auto", "small", "big"], default="auto")
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the captured CUDA graph (profiling)")
     ap.add_argument("--hidden", type=int, default=512)
     ap.add_argument("--grid", type=int, nargs="+", default=[64])
     ap.add_argument("--gate", choices=["emulator", "product_key"], default="emulator",
@@ -260,7 +261,7 @@ def _measure_ours(args, rank, world, local_rank, B, path="auto", tag="named", st
                      tokens_per_rank=B, capacity_factor=capacity, failure_rate=args.failure_rate,
                      gate_mode=args.gate, shadow_experts=args.shadow_experts, shadow_tol=args.shadow_tol,
                      expert_dtype=args.expert_dtype, expert_path=path)
-    trainer = DMoETrainer(cfg)
+    trainer = DMoETrainer(cfg, use_graph=False if args.no_graph else None)
     n_batches = 4
     xs_host, ys_host = synthetic_mnist(B, n_batches, seed=1234 + rank, in_features=cfg.in_features)
     xs_dev = [x.cuda(non_blocking=True) for x in xs_host]

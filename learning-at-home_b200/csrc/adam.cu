@@ -34,9 +34,11 @@ struct AdamArgs {
     // optional restriction to a subset of the segments (seg_mask != 0): the kernel then walks only the concatenation of the
     // selected segments (the fused wgrad+AMSGrad kernel of small_m.cu owns the weight matrices, this one the small vectors)
     int num_ranges; long long r_start[6]; long long r_cum[7];
+    const int* poison;   // status word: bit 0 set (a peer-flag wait timed out in this step) -> no update from partial data
 };
 
 __global__ void __launch_bounds__(256) adam_kernel(AdamArgs a) {
+    if (a.poison && (*a.poison & 1)) return;
     const long long stride = static_cast<long long>(gridDim.x) * blockDim.x * 4;
     const long long span = a.num_ranges ? a.r_cum[a.num_ranges] : a.total;
     for (long long j = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4; j < span; j += stride) {
@@ -138,6 +140,8 @@ __global__ void cast_bf16_kernel(const float* __restrict__ src, bf16* __restrict
 
 using namespace lah;
 
+extern "C" const int* lah_get_poison_word();
+
 extern "C" {
 
 int lah_adam_step(float* p, float* g, float* m, float* v, float* vmax, void* p_bf16, int num_segs,
@@ -165,6 +169,7 @@ int lah_adam_step(float* p, float* g, float* m, float* v, float* vmax, void* p_b
     a.zero_mask = zero_mask; a.world = world; a.peer_grad_off = peer_grad_off; a.grad_scale = grad_scale;
     a.G_active = G_active > 0 ? G_active : G; a.shadow_of = shadow_of; a.shadow_g_off = shadow_g_off; a.me = me;
     for (int i = 0; i < 8; ++i) a.peer_base[i] = (peer_bases && i < world) ? (char*)peer_bases[i] : nullptr;
+    a.poison = lah_get_poison_word();
     a.num_ranges = 0;
     a.r_cum[0] = 0;
     if (seg_mask) {   // adjacent selected segments merge into one range

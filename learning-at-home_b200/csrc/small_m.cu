@@ -84,7 +84,8 @@ constexpr int A_BYTES = BM * BK * 2;          // 16 KB
 constexpr int B_BYTES = BN_MAX * BK * 2;      // 16 KB (only box_rows * 128 B are filled)
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-constexpr int SMEM_TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 1024;
+constexpr int QD = 4;                         // depth of the tile queue (dynamic scheduler)
+constexpr int SMEM_TOTAL = BAR_OFFSET + (2 * STAGES + 4 + 2 * QD) * 8 + QD * 4 + 16 + 1024;
 
 struct Params {
     int G, M_out, K;          // groups, output features (rows of the weight operand), reduction length
@@ -99,10 +100,14 @@ struct Params {
     int wait_count, wait_epoch;
     const int* epoch_base;    // optional device-side epoch base added to wait_epoch (CUDA-graph replay)
     int* status;
+    int* tile_counter;        // work-stealing tile counter (zeroed before the launch)
 };
 
 __device__ __forceinline__ int box_rows_of(int nn) { return nn <= 16 ? 16 : (nn <= 32 ? 32 : (nn <= 64 ? 64 : 128)); }
 
+// Tiles are handed out DYNAMICALLY: SMs do not get equal shares of HBM bandwidth (ncu on the static version: SMs idle 15-20 %
+// of the kernel waiting for the slowest one), so the TMA-producer thread of every CTA draws the next (group, 128-row slice)
+// from a global counter and publishes it to the other roles of its CTA through a small smem queue.
 template <bool A_MN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 swapab_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB16,
@@ -114,7 +119,10 @@ swapab_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const __g
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tmem_full = empty_bar + STAGES;
     uint64_t* tmem_empty = tmem_full + 2;
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    uint64_t* q_full = tmem_empty + 2;
+    uint64_t* q_empty = q_full + QD;
+    volatile int* q_tile = reinterpret_cast<volatile int*>(q_empty + QD);
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(const_cast<int*>(q_tile) + QD);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -133,6 +141,10 @@ swapab_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const __g
             mbar_init(&tmem_full[i], 1);
             mbar_init(&tmem_empty[i], 4);
         }
+        for (int i = 0; i < QD; ++i) {
+            mbar_init(&q_full[i], 1);
+            mbar_init(&q_empty[i], 5);   // MMA thread + 4 epilogue warps
+        }
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc(tmem_ptr, 2 * BN_MAX);
@@ -146,7 +158,7 @@ swapab_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const __g
     const int num_kb = p.K / BK;
 
     if (warp == 0 && lane == 0) {
-        // =============================================================== TMA producer
+        // =============================================================== scheduler + TMA producer
         if (p.wait_flags) {
             const int epoch = p.wait_epoch + (p.epoch_base ? *p.epoch_base : 0);
             const unsigned long long t_wait = globaltimer_ns();
@@ -155,12 +167,27 @@ swapab_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const __g
             if (blockIdx.x == 0) atomicAdd(reinterpret_cast<unsigned long long*>(p.status + 2), globaltimer_ns() - t_wait);
             fence_proxy_async_global();
         }
-        int stage = 0;
-        uint32_t phase = 0;
-        for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        int stage = 0, qi = 0;
+        uint32_t phase = 0, qphase = 0;
+        while (true) {
+            int tile;
+            while (true) {   // draw the next tile of an ACTIVE group; a drawn tile of an empty group skips the whole group
+                tile = atomicAdd(p.tile_counter, 1);
+                if (tile >= total) break;
+                const int g = tile / m_slices;
+                if (__ldg(p.group_rows + g) > 0) break;
+                atomicMax(p.tile_counter, (g + 1) * m_slices);
+            }
+            mbar_wait(&q_empty[qi], qphase ^ 1);
+            q_tile[qi] = tile;
+            mbar_arrive(&q_full[qi]);
+            if (++qi == QD) {
+                qi = 0;
+                qphase ^= 1;
+            }
+            if (tile >= total) break;
             const int g = tile / m_slices, ms = tile - g * m_slices;
             const int rows = __ldg(p.group_rows + g);
-            if (rows <= 0) continue;
             const int off = __ldg(p.group_off + g);
             for (int n0 = 0; n0 < rows; n0 += BN_MAX) {
                 const int box = box_rows_of(min(rows - n0, BN_MAX));
@@ -190,13 +217,20 @@ swapab_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const __g
         // =============================================================== MMA issuer
         constexpr uint32_t A_LBO = A_MN ? BK * 128 : 0;
         constexpr uint32_t A_KSTEP = A_MN ? UMMA_K * 128 : UMMA_K * 2;
-        int stage = 0;
-        uint32_t phase = 0;
+        int stage = 0, qi = 0;
+        uint32_t phase = 0, qphase = 0;
         int iter = 0;
-        for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        while (true) {
+            mbar_wait(&q_full[qi], qphase);
+            const int tile = q_tile[qi];
+            mbar_arrive(&q_empty[qi]);
+            if (++qi == QD) {
+                qi = 0;
+                qphase ^= 1;
+            }
+            if (tile >= total) break;
             const int g = tile / m_slices;
             const int rows = __ldg(p.group_rows + g);
-            if (rows <= 0) continue;
             for (int n0 = 0; n0 < rows; n0 += BN_MAX) {
                 const int nn = min(rows - n0, BN_MAX);
                 const uint32_t n16 = static_cast<uint32_t>((nn + 15) & ~15);
@@ -230,11 +264,20 @@ swapab_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const __g
     } else if (warp >= 2) {
         // =============================================================== epilogue: thread = output feature, column = token
         const int lane_group = warp & 3;
-        int iter = 0;
-        for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        int iter = 0, qi = 0;
+        uint32_t qphase = 0;
+        while (true) {
+            mbar_wait(&q_full[qi], qphase);
+            const int tile = q_tile[qi];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&q_empty[qi]);
+            if (++qi == QD) {
+                qi = 0;
+                qphase ^= 1;
+            }
+            if (tile >= total) break;
             const int g = tile / m_slices, ms = tile - g * m_slices;
             const int rows = __ldg(p.group_rows + g);
-            if (rows <= 0) continue;
             const int off = __ldg(p.group_off + g);
             const int feat = ms * BM + lane_group * 32 + lane;
             const float bias = p.bias ? __ldg(p.bias + static_cast<long long>(g) * p.M_out + feat) : 0.f;
@@ -293,7 +336,9 @@ constexpr int STATE_TILE = 32 * 128;                     // 32 rows x 32 fp32 (o
 constexpr int SLOT_BYTES = 4 * STATE_TILE;               // p, m, v, vmax
 constexpr int STATE_OFFSET = OP_BYTES;
 constexpr int BAR_OFFSET = STATE_OFFSET + 4 * SLOTS * SLOT_BYTES;
-constexpr int SMEM_TOTAL = BAR_OFFSET + (2 + 4 + 4 * SLOTS) * 8 + 16 + 1024;
+constexpr int QD = 4;                                    // depth of the tile queue (dynamic scheduler)
+constexpr int CHUNKS = BN_MAX / 32;                      // 32-column chunks per tile
+constexpr int SMEM_TOTAL = BAR_OFFSET + (2 + 4 + 4 * SLOTS + 2 * QD) * 8 + QD * 4 + 16 + 1024;
 static_assert(SMEM_TOTAL <= 232448, "shared memory budget");
 
 struct Params {
@@ -305,43 +350,12 @@ struct Params {
     bf16* p_bf16;             // [G, N, K] bf16 mirror consumed by the GEMMs
     float lr, beta1, beta2, eps;
     int amsgrad;
+    int* tile_counter;        // work-stealing tile counter (zeroed before the launch)
+    const int* poison;        // optional status word: a step that timed out on a peer must not update anything
 };
 
-struct ChunkIter {   // enumerates (tile, 32-column chunk) of the active tiles of this CTA, in processing order
-    int tile, cc, g, mt, nt;
-    int total, tiles_per_group, n_tiles;
-    const Params* p;
-    __device__ __forceinline__ bool active(int t) {
-        const int gg = t / tiles_per_group;
-        if (__ldg(p->group_rows + gg) <= 0) return false;
-        if (p->skip && __ldg(p->skip + 2 * gg) >= 0) return false;
-        return true;
-    }
-    __device__ __forceinline__ void decode() {
-        g = tile / tiles_per_group;
-        const int r = tile - g * tiles_per_group;
-        mt = r / n_tiles;
-        nt = r - mt * n_tiles;
-    }
-    __device__ __forceinline__ void init(const Params* pp, int first, int step) {
-        p = pp;
-        n_tiles = pp->K / BN_MAX;
-        tiles_per_group = (pp->N / BM) * n_tiles;
-        total = pp->G * tiles_per_group;
-        tile = first;
-        cc = 0;
-        while (tile < total && !active(tile)) tile += step;
-        if (tile < total) decode();
-    }
-    __device__ __forceinline__ bool valid() const { return tile < total; }
-    __device__ __forceinline__ void next(int step) {
-        if (++cc == BN_MAX / 32) {
-            cc = 0;
-            tile += step;
-            while (tile < total && !active(tile)) tile += step;
-            if (tile < total) decode();
-        }
-    }
+struct Tile {
+    int g, mt, nt;
 };
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -355,10 +369,14 @@ wgrad_adam_kernel(const Params p, const __grid_constant__ CUtensorMap tmDY, cons
     uint64_t* tmem_full = op_empty + 1;     // [2]
     uint64_t* tmem_empty = tmem_full + 2;   // [2]
     uint64_t* st_full = tmem_empty + 2;     // [4 warps][SLOTS]
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(st_full + 4 * SLOTS);
+    uint64_t* q_full = st_full + 4 * SLOTS;
+    uint64_t* q_empty = q_full + QD;
+    volatile int* q_tile = reinterpret_cast<volatile int*>(q_empty + QD);
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(const_cast<int*>(q_tile) + QD);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    if (p.poison && (*p.poison & 1)) return;   // degraded step (a peer timed out): no optimizer step from partial data
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmDY);
@@ -374,6 +392,10 @@ wgrad_adam_kernel(const Params p, const __grid_constant__ CUtensorMap tmDY, cons
             mbar_init(&tmem_empty[i], 4);
         }
         for (int i = 0; i < 4 * SLOTS; ++i) mbar_init(&st_full[i], 1);
+        for (int i = 0; i < QD; ++i) {
+            mbar_init(&q_full[i], 1);
+            mbar_init(&q_empty[i], 5);   // MMA thread + 4 epilogue warps
+        }
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc(tmem_ptr, 2 * BN_MAX);
@@ -382,36 +404,71 @@ wgrad_adam_kernel(const Params p, const __grid_constant__ CUtensorMap tmDY, cons
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
+    const int n_tiles = p.K / BN_MAX;
+    const int tiles_per_group = (p.N / BM) * n_tiles;
+    const int total = p.G * tiles_per_group;
+    auto decode = [&](int tile) {
+        Tile t;
+        t.g = tile / tiles_per_group;
+        const int r = tile - t.g * tiles_per_group;
+        t.mt = r / n_tiles;
+        t.nt = r - t.mt * n_tiles;
+        return t;
+    };
+
     if (warp == 0 && lane == 0) {
-        // =============================================================== operand producer: dY^T / X^T k-blocks of 64 tokens
-        ChunkIter it;
-        it.init(&p, blockIdx.x, gridDim.x);
-        uint32_t phase = 0;
-        while (it.valid()) {
-            const int off = __ldg(p.group_off + it.g), rows = __ldg(p.group_rows + it.g);
+        // =============================================================== scheduler + operand producer (dY^T / X^T k-blocks)
+        // tiles are drawn from a global counter (work stealing: SMs see different HBM bandwidth, a static split leaves the
+        // fast ones idle for ~15 % of the kernel) and published to the MMA thread and the epilogue warps through a queue
+        uint32_t phase = 0, qphase = 0;
+        int qi = 0;
+        while (true) {
+            int tile;
+            while (true) {
+                tile = atomicAdd(p.tile_counter, 1);
+                if (tile >= total) break;
+                const int g = tile / tiles_per_group;
+                if (__ldg(p.group_rows + g) > 0 && !(p.skip && __ldg(p.skip + 2 * g) >= 0)) break;
+                atomicMax(p.tile_counter, (g + 1) * tiles_per_group);   // skip the rest of an inactive group
+            }
+            mbar_wait(&q_empty[qi], qphase ^ 1);
+            q_tile[qi] = tile;
+            mbar_arrive(&q_full[qi]);
+            if (++qi == QD) {
+                qi = 0;
+                qphase ^= 1;
+            }
+            if (tile >= total) break;
+            const Tile t = decode(tile);
+            const int off = __ldg(p.group_off + t.g), rows = __ldg(p.group_rows + t.g);
             for (int t0 = 0; t0 < rows; t0 += BK) {
                 mbar_wait(op_empty, phase ^ 1);
                 mbar_arrive_expect_tx(op_full, OP_BYTES);
                 uint8_t* sa = smem;
                 uint8_t* sb = smem + BK * BM * 2;
 #pragma unroll
-                for (int i = 0; i < BM / 64; ++i) tma_load_2d(sa + i * (BK * 128), &tmDY, op_full, it.mt * BM + i * 64, off + t0);
+                for (int i = 0; i < BM / 64; ++i) tma_load_2d(sa + i * (BK * 128), &tmDY, op_full, t.mt * BM + i * 64, off + t0);
 #pragma unroll
-                for (int i = 0; i < BN_MAX / 64; ++i) tma_load_2d(sb + i * (BK * 128), &tmX, op_full, it.nt * BN_MAX + i * 64, off + t0);
+                for (int i = 0; i < BN_MAX / 64; ++i) tma_load_2d(sb + i * (BK * 128), &tmX, op_full, t.nt * BN_MAX + i * 64, off + t0);
                 phase ^= 1;
             }
-            it.cc = BN_MAX / 32 - 1;   // jump to the next tile
-            it.next(gridDim.x);
         }
     } else if (warp == 1 && lane == 0) {
         // =============================================================== MMA issuer: only ceil(rows/16) k-steps of a block
         constexpr uint32_t idesc = make_idesc_bf16_f32(BM, BN_MAX, 1u, 1u);
-        ChunkIter it;
-        it.init(&p, blockIdx.x, gridDim.x);
-        uint32_t phase = 0;
-        int iter = 0;
-        while (it.valid()) {
-            const int rows = __ldg(p.group_rows + it.g);
+        uint32_t phase = 0, qphase = 0;
+        int iter = 0, qi = 0;
+        while (true) {
+            mbar_wait(&q_full[qi], qphase);
+            const int tile = q_tile[qi];
+            mbar_arrive(&q_empty[qi]);
+            if (++qi == QD) {
+                qi = 0;
+                qphase ^= 1;
+            }
+            if (tile >= total) break;
+            const Tile t = decode(tile);
+            const int rows = __ldg(p.group_rows + t.g);
             const int as = iter & 1;
             const uint32_t aphase = (iter >> 1) & 1;
             mbar_wait(&tmem_empty[as], aphase ^ 1);
@@ -433,8 +490,6 @@ wgrad_adam_kernel(const Params p, const __grid_constant__ CUtensorMap tmDY, cons
                 phase ^= 1;
             }
             ++iter;
-            it.cc = BN_MAX / 32 - 1;
-            it.next(gridDim.x);
         }
     } else if (warp >= 2) {
         // =============================================================== epilogue: state streaming + AMSGrad
@@ -442,53 +497,66 @@ wgrad_adam_kernel(const Params p, const __grid_constant__ CUtensorMap tmDY, cons
         uint8_t* ring = smem + STATE_OFFSET + (warp - 2) * SLOTS * SLOT_BYTES;
         uint64_t* full = st_full + (warp - 2) * SLOTS;
         const int n_state = p.amsgrad ? 4 : 3;
-        auto issue_load = [&](const ChunkIter& c, int slot) {   // lane 0 only
+        // chunk n of this CTA = 32-column chunk (n % CHUNKS) of the (n / CHUNKS)-th tile drawn from the queue; the loads run
+        // two chunks ahead of the update, so at most two tiles are live: fifo[(n / CHUNKS) & 1]
+        Tile fifo[2];
+        int fetched = 0, qi = 0;
+        uint32_t qphase = 0;
+        bool drained = false;
+        auto have_chunk = [&](int n) -> bool {
+            while (!drained && n / CHUNKS >= fetched) {
+                mbar_wait(&q_full[qi], qphase);
+                const int tile = q_tile[qi];
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&q_empty[qi]);
+                if (++qi == QD) {
+                    qi = 0;
+                    qphase ^= 1;
+                }
+                if (tile >= total) {
+                    drained = true;
+                } else {
+                    fifo[fetched & 1] = decode(tile);
+                    ++fetched;
+                }
+            }
+            return n / CHUNKS < fetched;
+        };
+        auto issue_load = [&](int n) {   // lane 0 only
+            const Tile& t = fifo[(n / CHUNKS) & 1];
+            const int cc = n % CHUNKS, slot = n % SLOTS;
             uint8_t* s = ring + slot * SLOT_BYTES;
-            const int col = c.nt * BN_MAX + c.cc * 32;
-            const int row = c.g * p.N + c.mt * BM + q * 32;
+            const int col = t.nt * BN_MAX + cc * 32;
+            const int row = t.g * p.N + t.mt * BM + q * 32;
             mbar_arrive_expect_tx(&full[slot], n_state * STATE_TILE);
             tma_load_2d(s, &tmP, &full[slot], col, row);
             tma_load_2d(s + STATE_TILE, &tmM, &full[slot], col, row);
             tma_load_2d(s + 2 * STATE_TILE, &tmV, &full[slot], col, row);
             if (p.amsgrad) tma_load_2d(s + 3 * STATE_TILE, &tmVM, &full[slot], col, row);
         };
-        ChunkIter cur, pre;
-        cur.init(&p, blockIdx.x, gridDim.x);
-        pre = cur;
-        int n_loaded = 0;   // chunks whose loads were issued
-        if (lane == 0) {
-            for (int i = 0; i < SLOTS - 1 && pre.valid(); ++i) {
-                issue_load(pre, n_loaded % SLOTS);
-                ++n_loaded;
-                pre.next(gridDim.x);
-            }
-        }
-        int c = 0, iter = 0;
+        for (int n = 0; n < SLOTS - 1; ++n)
+            if (have_chunk(n) && lane == 0) issue_load(n);
         float step_size = 0.f, inv_sqrt_bc2 = 0.f;
-        while (cur.valid()) {
-            const int slot = c % SLOTS;
+        for (int c = 0; have_chunk(c); ++c) {
+            const Tile t = fifo[(c / CHUNKS) & 1];
+            const int cc = c % CHUNKS, slot = c % SLOTS, iter = c / CHUNKS, as = iter & 1;
             const uint32_t sphase = (c / SLOTS) & 1;
-            const int as = iter & 1;
-            if (cur.cc == 0) {
-                const float st = static_cast<float>(__ldg(p.step + cur.g));
+            if (cc == 0) {
+                const float st = static_cast<float>(__ldg(p.step + t.g));
                 step_size = p.lr / (1.f - powf(p.beta1, st));
                 inv_sqrt_bc2 = rsqrtf(1.f - powf(p.beta2, st));
                 mbar_wait(&tmem_full[as], (iter >> 1) & 1);
                 tcgen05_fence_after();
             }
-            if (lane == 0) {
-                // slot (c-1) % SLOTS is refilled with chunk c + SLOTS - 1: its previous contents (chunk c-1) must have been read
-                // by the TMA store engine
-                if (pre.valid()) {
-                    tma_store_wait_read<0>();
-                    issue_load(pre, n_loaded % SLOTS);
-                    ++n_loaded;
-                    pre.next(gridDim.x);
-                }
+            // slot (c-1) % SLOTS is refilled with chunk c + SLOTS - 1: its previous contents (chunk c-1) must have been read by
+            // the TMA store engine
+            if (have_chunk(c + SLOTS - 1) && lane == 0) {
+                tma_store_wait_read<0>();
+                issue_load(c + SLOTS - 1);
             }
             mbar_wait(&full[slot], sphase);
             uint32_t r[32];
-            tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN_MAX + cur.cc * 32, r);
+            tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN_MAX + cc * 32, r);
             tmem_ld_wait();
             uint8_t* s = ring + slot * SLOT_BYTES + lane * 128;
             uint32_t packed[16];
@@ -501,18 +569,18 @@ wgrad_adam_kernel(const Params p, const __grid_constant__ CUtensorMap tmDY, cons
                 float4 vm = p.amsgrad ? *reinterpret_cast<float4*>(s + 3 * STATE_TILE + o) : make_float4(0.f, 0.f, 0.f, 0.f);
                 float* pp = &pw.x; float* mp = &m.x; float* vp = &v.x; float* vmp = &vm.x;
 #pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    const float grad = __uint_as_float(r[4 * j + t]);
-                    mp[t] = mp[t] + (1.f - p.beta1) * (grad - mp[t]);
-                    vp[t] = vp[t] * p.beta2 + (1.f - p.beta2) * grad * grad;
+                for (int e = 0; e < 4; ++e) {
+                    const float grad = __uint_as_float(r[4 * j + e]);
+                    mp[e] = mp[e] + (1.f - p.beta1) * (grad - mp[e]);
+                    vp[e] = vp[e] * p.beta2 + (1.f - p.beta2) * grad * grad;
                     float denom;
                     if (p.amsgrad) {
-                        vmp[t] = fmaxf(vmp[t], vp[t]);
-                        denom = sqrtf(vmp[t]) * inv_sqrt_bc2 + p.eps;
+                        vmp[e] = fmaxf(vmp[e], vp[e]);
+                        denom = sqrtf(vmp[e]) * inv_sqrt_bc2 + p.eps;
                     } else {
-                        denom = sqrtf(vp[t]) * inv_sqrt_bc2 + p.eps;
+                        denom = sqrtf(vp[e]) * inv_sqrt_bc2 + p.eps;
                     }
-                    pp[t] -= step_size * (mp[t] / denom);
+                    pp[e] -= step_size * (mp[e] / denom);
                 }
                 *reinterpret_cast<float4*>(s + o) = pw;
                 *reinterpret_cast<float4*>(s + STATE_TILE + o) = m;
@@ -522,8 +590,8 @@ wgrad_adam_kernel(const Params p, const __grid_constant__ CUtensorMap tmDY, cons
                 packed[2 * j + 1] = pack_bf16x2(pw.z, pw.w);
             }
             {   // bf16 mirror: 64 B per thread straight from registers
-                const long long row = static_cast<long long>(cur.g) * p.N + cur.mt * BM + q * 32 + lane;
-                int4* dst = reinterpret_cast<int4*>(p.p_bf16 + row * p.K + cur.nt * BN_MAX + cur.cc * 32);
+                const long long row = static_cast<long long>(t.g) * p.N + t.mt * BM + q * 32 + lane;
+                int4* dst = reinterpret_cast<int4*>(p.p_bf16 + row * p.K + t.nt * BN_MAX + cc * 32);
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
                     dst[j] = make_int4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
@@ -532,22 +600,19 @@ wgrad_adam_kernel(const Params p, const __grid_constant__ CUtensorMap tmDY, cons
             __syncwarp();
             if (lane == 0) {
                 uint8_t* sb = ring + slot * SLOT_BYTES;
-                const int col = cur.nt * BN_MAX + cur.cc * 32;
-                const int row = cur.g * p.N + cur.mt * BM + q * 32;
+                const int col = t.nt * BN_MAX + cc * 32;
+                const int row = t.g * p.N + t.mt * BM + q * 32;
                 tma_store_2d(&tmP, sb, col, row);
                 tma_store_2d(&tmM, sb + STATE_TILE, col, row);
                 tma_store_2d(&tmV, sb + 2 * STATE_TILE, col, row);
                 if (p.amsgrad) tma_store_2d(&tmVM, sb + 3 * STATE_TILE, col, row);
                 tma_store_commit();
             }
-            if (cur.cc == BN_MAX / 32 - 1) {   // accumulator fully drained
+            if (cc == CHUNKS - 1) {   // accumulator fully drained
                 tcgen05_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tmem_empty[as]);
-                ++iter;
             }
-            ++c;
-            cur.next(gridDim.x);
         }
         if (lane == 0) tma_store_wait<0>();   // all state tiles are in global memory before the CTA exits
     }
@@ -568,7 +633,25 @@ using namespace lah::smallm;
 
 extern "C" const int* lah_get_epoch_base();
 
+// work-stealing tile counter shared by the launches of this file (stream-ordered: memset -> kernel); allocated on first use
+static int* tile_counter() {
+    static int* ctr = nullptr;
+    if (!ctr) {
+        if (cudaMalloc(&ctr, 256) != cudaSuccess) return nullptr;
+        cudaMemset(ctr, 0, 256);
+    }
+    return ctr;
+}
+static const int* g_poison = nullptr;
+
 extern "C" {
+
+// status word whose bit 0 (a peer-flag wait timed out in this step) turns the optimizer kernels into no-ops; NULL disables
+int lah_set_poison_word(const int* status) {
+    g_poison = status;
+    return 0;
+}
+const int* lah_get_poison_word() { return g_poison; }
 
 // out[row, :] = act_rows[row, :] @ W[g]^T (+bias[g]) (+residual[row, :]) for the rows of every group, swap-AB tiles.
 //   a_mn == 0: W is [G, M_out, K] (forward);  a_mn == 1: W is [G, K, M_out] and the product is x @ W (dgrad)
@@ -603,8 +686,11 @@ int lah_swapab_linear(const void* x, long long ldx, int x_rows, const void* W, i
     p.G = G; p.M_out = M_out; p.K = K; p.group_off = group_off; p.group_rows = group_rows; p.out = (bf16*)out; p.ldo = ldo;
     p.bias = bias; p.residual = (const bf16*)residual; p.ldr = ldr; p.wait_flags = wait_flags; p.wait_count = wait_count;
     p.wait_epoch = wait_epoch; p.epoch_base = epoch_base ? epoch_base : lah_get_epoch_base(); p.status = status;
+    p.tile_counter = tile_counter();
+    if (!p.tile_counter) return -3;
     const int total = G * (M_out / BM);
     if (total <= 0) return 0;
+    if (cudaMemsetAsync(p.tile_counter, 0, sizeof(int), st) != cudaSuccess) return -4;
     int ctas = num_sms();
     if (max_ctas > 0 && max_ctas < ctas) ctas = max_ctas;
     if (total < ctas) ctas = total;
@@ -659,8 +745,12 @@ int lah_wgrad_adam(const void* dy, long long lddy, const void* x, long long ldx,
     wa::Params a;
     a.G = G; a.N = N; a.K = K; a.group_off = group_off; a.group_rows = group_rows; a.skip = skip; a.step = step;
     a.p_bf16 = (bf16*)p_bf16; a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.amsgrad = amsgrad;
+    a.tile_counter = tile_counter() ? tile_counter() + 16 : nullptr;   // own word (64 B apart from the GEMM's)
+    a.poison = g_poison;
+    if (!a.tile_counter) return -3;
     const long long total = 1ll * G * (N / BM) * (K / BN_MAX);
     if (total <= 0) return 0;
+    if (cudaMemsetAsync(a.tile_counter, 0, sizeof(int), st) != cudaSuccess) return -4;
     int ctas = num_sms();
     if (max_ctas > 0 && max_ctas < ctas) ctas = max_ctas;
     if (total < ctas) ctas = (int)total;

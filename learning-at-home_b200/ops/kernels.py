@@ -32,6 +32,7 @@ def _lib():
         "lah_grouped_colsum_t": [P, L, P, I, P, I, I, P],
         "lah_set_step_counters": [P],
         "lah_set_multicast": [c_ull],
+        "lah_set_poison_word": [P],
         "lah_nvls_allreduce": [L, L, Fl, P],
         "lah_heartbeat": [L, I, I, L, P],
         "lah_alive_from_heartbeats": [P, P, I, L, L, P],
@@ -149,6 +150,11 @@ def alive_from_heartbeats(hb, alive, now_ms, max_age_ms):
     native.check(_lib().lah_alive_from_heartbeats(ptr(hb), ptr(alive), alive.numel(), int(now_ms), int(max_age_ms),
                                                   stream_ptr()), "lah_alive_from_heartbeats")
     native.count_launch()
+
+
+def set_poison_word(status):
+    """int32 status tensor whose bit 0 (STATUS_TIMEOUT) disables every optimizer kernel of the step (None: never)"""
+    native.check(_lib().lah_set_poison_word(ptr(status)), "lah_set_poison_word")
 
 
 def set_step_counters(ctr):

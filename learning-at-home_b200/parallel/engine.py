@@ -180,6 +180,7 @@ class EngineContext:
         self.step_ctr = torch.zeros(4, **i32)
         K.set_step_counters(self.step_ctr)
         K.set_spin_timeout_ms(cfg.peer_timeout_ms)
+        K.set_poison_word(self.status)   # a step in which a peer timed out applies no optimizer update (the batch fails)
         assert 2 * cfg.num_layers + 4 < self.EPOCH_STRIDE
         self.alive = torch.ones(self.E, dtype=torch.uint8, device=self.device)
         # device-resident expert index shared by ALL ranks ("DHT collapse"): hb[e] = last heartbeat (ms) of expert
@@ -207,6 +208,7 @@ class EngineContext:
         invalid, so call it only when the trainer / layers of this context are no longer used."""
         K.set_wait_counter(None)
         K.set_step_counters(None)
+        K.set_poison_word(None)
         self.heap.close()
 
     # ------------------------------------------------------------------ liveness (heartbeat -> device table -> gate kernel)
