@@ -34,6 +34,7 @@ struct AdamArgs {
     // optional restriction to a subset of the segments (seg_mask != 0): the kernel then walks only the concatenation of the
     // selected segments (the fused wgrad+AMSGrad kernel of small_m.cu owns the weight matrices, this one the small vectors)
     int num_ranges; long long r_start[6]; long long r_cum[7];
+    int dead_mask;       // ranks excluded from the peer gradient reduce (their buffers hold stale data)
     const int* poison;   // status word: bit 0 set (a peer-flag wait timed out in this step) -> no update from partial data
 };
 
@@ -66,6 +67,7 @@ __global__ void __launch_bounds__(256) adam_kernel(AdamArgs a) {
         if (a.peer_grad_off >= 0) {
             gr = make_float4(0.f, 0.f, 0.f, 0.f);
             for (int r = 0; r < a.world; ++r) {
+                if ((a.dead_mask >> r) & 1) continue;
                 const float4 t = *reinterpret_cast<const float4*>(
                     reinterpret_cast<const float*>(a.peer_base[r] + a.peer_grad_off) + i);
                 gr.x += t.x; gr.y += t.y; gr.z += t.z; gr.w += t.w;
@@ -149,7 +151,7 @@ int lah_adam_step(float* p, float* g, float* m, float* v, float* vmax, void* p_b
                   const int* step, const int* group_rows, int step_scalar, float lr, float beta1, float beta2, float eps,
                   float weight_decay, int amsgrad, int zero_mask, int world, long long peer_grad_off,
                   const unsigned long long* peer_bases, float grad_scale, int G_active, const int* shadow_of,
-                  long long shadow_g_off, int me, int seg_mask, cudaStream_t st) {
+                  long long shadow_g_off, int me, int seg_mask, int dead_mask, cudaStream_t st) {
     if (num_segs < 1 || num_segs > 12) return -2;
     AdamArgs a;
     a.num_segs = num_segs;
@@ -170,6 +172,7 @@ int lah_adam_step(float* p, float* g, float* m, float* v, float* vmax, void* p_b
     a.G_active = G_active > 0 ? G_active : G; a.shadow_of = shadow_of; a.shadow_g_off = shadow_g_off; a.me = me;
     for (int i = 0; i < 8; ++i) a.peer_base[i] = (peer_bases && i < world) ? (char*)peer_bases[i] : nullptr;
     a.poison = lah_get_poison_word();
+    a.dead_mask = dead_mask;
     a.num_ranges = 0;
     a.r_cum[0] = 0;
     if (seg_mask) {   // adjacent selected segments merge into one range

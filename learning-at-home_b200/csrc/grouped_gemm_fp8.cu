@@ -154,7 +154,8 @@ gemm_fp8_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const _
         if (p.wait_flags) {
             const unsigned long long t_wait = globaltimer_ns();
             for (int sidx = 0; sidx < p.wait_count; ++sidx)
-                if (!spin_flag_ge(p.wait_flags + sidx, p.wait_epoch + (p.epoch_base ? *p.epoch_base : 0))) atomicOr(p.status, 1);
+                spin_flag_ft(p.wait_flags + sidx, p.wait_epoch + (p.epoch_base ? p.epoch_base[0] : 0), p.status, sidx,
+                             p.epoch_base ? p.epoch_base[1] : 0);
             // exposed communication wait (ns) of this rank: status[2..3] is a 64-bit counter (EngineContext.wait_ns)
             if (blockIdx.x == 0) atomicAdd(reinterpret_cast<unsigned long long*>(p.status + 2), globaltimer_ns() - t_wait);
             fence_proxy_async_global();

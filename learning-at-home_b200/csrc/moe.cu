@@ -85,7 +85,14 @@ __device__ __forceinline__ float hash_uniform(unsigned long long x) {
     return static_cast<float>(x >> 40) * (1.0f / 16777216.0f);
 }
 
-__device__ __forceinline__ bool spin_until_ge(const int* flag, int epoch, int* status, int timeout_ms = 0) {
+// rank: the peer whose flag this is.  Excluded ranks (status[1] bit) are never waited for; once a wait of this step timed
+// out (status[0] bit 0) the remaining waits return at once — the step is abandoned, its optimizer updates are skipped
+__device__ __forceinline__ bool spin_until_ge(const int* flag, int epoch, int* status, int timeout_ms = 0, int rank = -1) {
+    if (status && rank >= 0) {
+        const volatile int* vs = status;
+        if ((vs[1] >> rank) & 1) return false;
+        if (vs[0] & STATUS_TIMEOUT) return false;
+    }
     const long long t0 = clock64();
     const long long limit = timeout_ms > 0 ? static_cast<long long>(timeout_ms) * 2000000ll : SPIN_TIMEOUT_CYCLES;
     while (ld_acquire_sys(flag) < epoch) {
@@ -296,8 +303,18 @@ __global__ void __launch_bounds__(1024) layout_exchange_kernel(Peers peers, Layo
         // 2. wait for everybody's counts
         const int* fw = reinterpret_cast<const int*>(peers.base[me] + a.flags_off) + a.slot * MAX_WORLD + tid;
         const unsigned long long t0 = globaltimer_ns();
-        spin_until_ge(fw, a.epoch, a.status, peers.spin_timeout_ms);
+        spin_until_ge(fw, a.epoch, a.status, peers.spin_timeout_ms, tid);
         account_wait(peers, t0, world);
+    }
+    __syncthreads();
+    {   // excluded ranks (host-maintained mask in status[1]) contribute no rows: their (stale) count rows read as zero
+        const int dead = reinterpret_cast<volatile int*>(a.status)[1];
+        if (dead) {
+            int* mine = reinterpret_cast<int*>(peers.base[me] + a.cnt_all_off);
+            for (int r = 0; r < world; ++r)
+                if ((dead >> r) & 1)
+                    for (int e = tid; e < a.E; e += blockDim.x) mine[static_cast<long long>(r) * a.E + e] = 0;
+        }
     }
     for (int t = tid; t < a.max_tiles; t += blockDim.x) a.tile_group[t] = -1;
     if (tid < MAX_WORLD) s_load[tid] = 0;
@@ -606,7 +623,7 @@ __global__ void signal_wait_kernel(Peers peers, long long flags_off, int slot, i
     if (do_wait && lane < peers.world) {
         const int* f = reinterpret_cast<const int*>(peers.base[peers.me] + flags_off) + slot * MAX_WORLD + lane;
         const unsigned long long t0 = globaltimer_ns();
-        spin_until_ge(f, epoch, status, peers.spin_timeout_ms);
+        spin_until_ge(f, epoch, status, peers.spin_timeout_ms, lane);
         account_wait(peers, t0, peers.world);
     }
 }
@@ -691,7 +708,7 @@ __global__ void __launch_bounds__(256) combine_rows_kernel(Peers peers, CombineA
         if (threadIdx.x < peers.world) {
             const int* f = reinterpret_cast<const int*>(peers.base[peers.me] + a.flags_off) + a.slot * MAX_WORLD + threadIdx.x;
             const unsigned long long t0 = globaltimer_ns();
-            spin_until_ge(f, a.epoch, a.status, peers.spin_timeout_ms);
+            spin_until_ge(f, a.epoch, a.status, peers.spin_timeout_ms, threadIdx.x);
             if (blockIdx.x == 0) account_wait(peers, t0, peers.world);
         }
         __syncthreads();

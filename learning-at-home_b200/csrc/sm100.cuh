@@ -292,6 +292,25 @@ __device__ __forceinline__ bool spin_flag_ge(const int* flag, int epoch) {
     }
     return true;
 }
+// Fault-tolerant flag wait used by the kernels that fuse the receive-side wait (GEMM producers).  status[0] bit 0 = "a wait
+// timed out in this step" (the step is then abandoned: later waits return at once and the optimizer kernels skip their
+// update), status[1] = bit mask of EXCLUDED ranks (host-decided from the heartbeat table): their flags are never waited for.
+__device__ __forceinline__ bool spin_flag_ft(const int* flag, int epoch, int* status, int rank, int timeout_ms) {
+    if (status) {
+        const volatile int* vs = status;
+        if ((vs[1] >> rank) & 1) return false;
+        if (vs[0] & 1) return false;
+    }
+    const long long t0 = clock64();
+    const long long limit = timeout_ms > 0 ? static_cast<long long>(timeout_ms) * 2000000ll : 20000000000ll;
+    while (ld_acquire_sys(flag) < epoch) {
+        if (clock64() - t0 > limit) {
+            if (status) atomicOr(status, 1);
+            return false;
+        }
+    }
+    return true;
+}
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));

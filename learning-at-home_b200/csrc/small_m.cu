@@ -163,7 +163,7 @@ swapab_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const __g
             const int epoch = p.wait_epoch + (p.epoch_base ? *p.epoch_base : 0);
             const unsigned long long t_wait = globaltimer_ns();
             for (int sidx = 0; sidx < p.wait_count; ++sidx)
-                if (!spin_flag_ge(p.wait_flags + sidx, epoch)) atomicOr(p.status, 1);
+                spin_flag_ft(p.wait_flags + sidx, epoch, p.status, sidx, p.epoch_base ? p.epoch_base[1] : 0);
             if (blockIdx.x == 0) atomicAdd(reinterpret_cast<unsigned long long*>(p.status + 2), globaltimer_ns() - t_wait);
             fence_proxy_async_global();
         }

@@ -81,6 +81,10 @@ class DMoEConfig:
     # backward batch (lib/runtime/expert_backend.py:95-97), the default.
     update_every_inputs: int = 0
     update_every_steps: int = 0
+    # stale trainer gradients (reference notebooks, cell 3: a trainer computes the gradients of the non-expert parameters,
+    # sleeps delay_ms and applies them `delay_steps` updates later): the trainer-side optimizer applies the gradient computed
+    # `trainer_staleness` steps ago; experts keep updating themselves immediately, exactly like the reference
+    trainer_staleness: int = 0
     # peer-flag wait timeout in ms (0 = ~10 s).  On expiry the waiting rank marks the step degraded (status bit) and goes on
     # with whatever arrived — the fused-path analogue of run_and_await_k's timeout_after_k_min (lib/utils/threading.py:76-125)
     peer_timeout_ms: int = 0
@@ -180,6 +184,8 @@ class EngineContext:
         self.step_ctr = torch.zeros(4, **i32)
         K.set_step_counters(self.step_ctr)
         K.set_spin_timeout_ms(cfg.peer_timeout_ms)
+        self.step_ctr[1] = int(cfg.peer_timeout_ms)   # the GEMM producers read the timeout from the same device words
+        self.dead_mask = 0                            # ranks excluded from every flag wait / reduce (host-decided)
         K.set_poison_word(self.status)   # a step in which a peer timed out applies no optimizer update (the batch fails)
         assert 2 * cfg.num_layers + 4 < self.EPOCH_STRIDE
         self.alive = torch.ones(self.E, dtype=torch.uint8, device=self.device)
@@ -232,6 +238,45 @@ class EngineContext:
             self._hb_stream = torch.cuda.Stream(self.device)
         with torch.cuda.stream(self._hb_stream):
             K.alive_from_heartbeats(self.hb, self.alive, now_ms, int(heartbeat_expiration * 1000))
+            self._apply_dead_mask()
+
+    # ------------------------------------------------------------------ failures: bounded waits, excluded ranks
+    def step_failed(self) -> bool:
+        """did a peer-flag wait time out since the last clear_failure()?  (synchronises).  A failed step applied NO optimizer
+        update (the kernels check the status word) — the batch is lost, like a GatingFunction call with fewer than k_min
+        responders (/root/reference/lib/utils/threading.py:120-125), the job is not."""
+        return bool(int(self.status.item()) & K.STATUS_TIMEOUT)
+
+    def clear_failure(self):
+        self._status_buf[0] = 0
+
+    def detect_dead_ranks(self, max_age: float, now: Optional[float] = None):
+        """ranks none of whose experts sent a heartbeat during the last ``max_age`` seconds (every rank reads the SAME
+        device-resident table, so the survivors agree without talking to each other)"""
+        ages = self.heartbeat_ages(now).view(self.world, self.E_loc)
+        return [r for r in range(self.world) if r != self.rank and float(ages[r].min()) > max_age]
+
+    def exclude_ranks(self, ranks):
+        """stop waiting for / reducing over ``ranks``: their flags are skipped by every wait, their dispatch counts read as
+        zero, their experts disappear from the gate (softmax renormalises over the survivors), trainer gradients are
+        averaged over the remaining ranks.  All survivors must exclude the same set (see detect_dead_ranks)."""
+        for r in ranks:
+            self.dead_mask |= 1 << int(r)
+        self._status_buf[1] = self.dead_mask
+        self._apply_dead_mask()
+        self.clear_failure()
+
+    def readmit_ranks(self, ranks):
+        for r in ranks:
+            self.dead_mask &= ~(1 << int(r))
+        self._status_buf[1] = self.dead_mask
+
+    def _apply_dead_mask(self):
+        if self.dead_mask:
+            view = self.alive.view(self.world, self.E_loc)
+            for r in range(self.world):
+                if (self.dead_mask >> r) & 1:
+                    view[r] = 0
 
     def heartbeat_ages(self, now: Optional[float] = None) -> torch.Tensor:
         """seconds since the last heartbeat of every expert (inf = never declared); synchronises"""

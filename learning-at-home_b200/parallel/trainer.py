@@ -84,6 +84,7 @@ class DMoETrainer:
     def close(self):
         """flush the metrics log and release the peer-mapped symmetric heap (GPU runs); idempotent"""
         self.metrics.close()
+        self.stop_heartbeats()
         if self.cuda and self.ctx is not None:
             torch.cuda.synchronize(self.device)
             self.ctx.close()
@@ -118,6 +119,8 @@ class DMoETrainer:
             off += p.numel()
         self.num_trainer_params = n
         self._n_pad = n_pad
+        d = int(self.cfg.trainer_staleness)
+        self._stale_ring = torch.zeros(d, n_pad, device=dev) if d > 0 else None
         if self.cuda:
             self.ctx.heap.barrier()
 
@@ -134,7 +137,19 @@ class DMoETrainer:
             return
         c = self.ctx
         K.bump_steps(self.step_dev, self._one)
-        if c.world > 1 and c.heap.mc_base:
+        if c.world > 1 and c.dead_mask:
+            # degraded mode: some ranks are excluded -> P2P gradient reduce over the survivors only (the switch reduction would
+            # include the stale buffers of the excluded ranks)
+            alive = c.world - bin(c.dead_mask).count("1")
+            epoch = c.next_epoch()
+            K.signal_wait(c.flags_off, K.SLOT_TRAINER, epoch, c.status, signal=True, wait=True)
+            K.adam_step(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.flat_vmax, None, [self._n_pad], 1,
+                        step=self.step_dev, lr=cfg.lr, betas=cfg.betas, eps=cfg.eps, amsgrad=cfg.amsgrad,
+                        world=c.world, peer_grad_off=self.flat_g_off, peer_bases=c.heap.peer_bases,
+                        grad_scale=1.0 / alive, dead_mask=c.dead_mask)
+            K.signal_wait(c.flags_off, K.SLOT_BARRIER, epoch, c.status, signal=True, wait=True)
+            self.flat_g.zero_()
+        elif c.world > 1 and c.heap.mc_base:
             # NVLS: gradients complete everywhere -> in-switch all-reduce (multimem.ld_reduce + multimem.st, every rank gets the
             # bit-identical mean) -> all slices written -> plain local AMSGrad that also zeroes the gradient buffer
             epoch = c.next_epoch()
@@ -209,6 +224,14 @@ class DMoETrainer:
                 block.apply_expert_gradients_ref()
         if timer is not None:
             timer.mark("trainer_bwd(stem+gates)")
+        if self._stale_ring is not None:
+            # delay line of trainer gradients: apply the gradient of `trainer_staleness` steps ago (static buffers: graph-safe)
+            with torch.no_grad():
+                oldest = self._stale_ring[0].clone()
+                if self._stale_ring.shape[0] > 1:
+                    self._stale_ring[:-1] = self._stale_ring[1:].clone()
+                self._stale_ring[-1].copy_(self.flat_g)
+                self.flat_g.copy_(oldest)
         self._trainer_optimizer_step()
         if timer is not None:
             timer.mark("trainer_adam")
@@ -280,6 +303,43 @@ class DMoETrainer:
         done = torch.cuda.Event()
         done.record(stream)
         return PendingLoss(event=done, host=host)
+
+    # ------------------------------------------------------------------ failure detection / recovery on the fused path
+    def start_heartbeats(self, period: float = 1.0):
+        """background thread: every ``period`` s declare this rank's experts alive in the device-resident table of every rank
+        (the in-box NetworkHandlerThread, /root/reference/lib/server/network_handler.py:17-20)"""
+        import threading
+        if getattr(self, "_hb_thread", None) is not None:
+            return
+        self._hb_stop = threading.Event()
+
+        def loop():
+            torch.cuda.set_device(self.device)
+            while not self._hb_stop.wait(period):
+                self.ctx.heartbeat()
+
+        self.ctx.heartbeat()
+        self._hb_thread = threading.Thread(target=loop, daemon=True, name="lah-heartbeat")
+        self._hb_thread.start()
+
+    def stop_heartbeats(self):
+        if getattr(self, "_hb_thread", None) is not None:
+            self._hb_stop.set()
+            self._hb_thread.join(timeout=5)
+            self._hb_thread = None
+
+    def step_failed(self) -> bool:
+        return bool(self.cuda and self.ctx.step_failed())
+
+    def recover(self, max_age: float = 5.0):
+        """after a failed step: exclude the ranks whose heartbeats stopped (all survivors read the same table and reach the
+        same verdict) and resume training over the surviving ranks / experts.  Returns the excluded ranks."""
+        dead = self.ctx.detect_dead_ranks(max_age)
+        self.ctx.exclude_ranks(dead)     # also clears the failure flag
+        self._graph, self._eager_steps = None, 2   # kernel arguments changed (reduce set): re-capture at the next step
+        for block in self.model.blocks:
+            block.release_workspace()
+        return dead
 
     # ------------------------------------------------------------------ liveness (failure detection / emulation, SURVEY 5.3)
     @torch.no_grad()

@@ -113,3 +113,25 @@ def test_rpc_throughput_baseline_two_processes():
     assert all(p.returncode == 0 for p in procs), outs
     line = [l for l in outs[0].splitlines() if l.startswith("RESULT")][0]
     assert "None" not in line and float(line.split("(")[1].split(",")[0]) > 0
+
+
+def test_convergence_notebooks_execute_in_smoke_mode(tmp_path, monkeypatch):
+    """the three notebooks are real experiments (config -> model -> async trainers -> curve -> pickle): run their code cells"""
+    import glob
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    monkeypatch.setenv("LAH_NB_SMOKE", "1")
+    monkeypatch.setenv("LAH_NB_LOGDIR", str(tmp_path))
+    monkeypatch.chdir(root)
+    notebooks = sorted(glob.glob(os.path.join(root, "learning-at-home_b200", "experiments", "convergence", "*.ipynb")))
+    assert len(notebooks) == 3
+    for path in notebooks:
+        nb = json.load(open(path))
+        cells = ["".join(c["source"]) for c in nb["cells"] if c["cell_type"] == "code"]
+        assert len(cells) >= 4
+        scope = {"__file__": path}
+        for src in cells:
+            exec(compile(src, os.path.basename(path), "exec"), scope)
+        assert len(scope["train_history"]) >= 6 and scope["val_history"] and "acc" in scope["val_history"][-1]
+    assert len(list(tmp_path.iterdir())) == 3

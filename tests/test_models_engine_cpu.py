@@ -296,3 +296,21 @@ def test_fast_nccl_baseline_formulation_learns_on_cpu():
         x, y = torch.randn(32, 12), torch.randint(0, 10, (32,))
         losses = [float(tr.train_step_device(x, y)) for _ in range(25)]
         assert losses[-1] < 0.6 * losses[0], losses
+
+
+def test_stale_trainer_gradients_and_update_every_on_cpu():
+    """asynchrony knobs of the engine (reference: notebooks' delay_steps, dmoe_emulator.py:70-77)"""
+    torch.manual_seed(0)
+    cfg = E.DMoEConfig(hidden=32, grid_size=(2, 2), k=2, num_layers=1, in_features=12, tokens_per_rank=32, lr=3e-3,
+                       trainer_staleness=2)
+    tr = DMoETrainer(cfg)
+    x, y = torch.randn(32, 12), torch.randint(0, 10, (32,))
+    w0 = tr.model.head.weight.detach().clone()
+    tr.train_step(x, y)
+    tr.train_step(x, y)
+    assert torch.equal(tr.model.head.weight, w0)          # the first two gradients are still in the delay line
+    assert int(tr.model.blocks[0].shard.step.max()) == 2  # experts do not wait for anybody
+    tr.train_step(x, y)
+    assert not torch.equal(tr.model.head.weight, w0)      # ... the gradient of step 0 arrives with step 2
+    losses = [tr.train_step(x, y) for _ in range(40)]
+    assert losses[-1] < 0.7 * losses[0]
