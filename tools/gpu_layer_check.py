@@ -216,7 +216,11 @@ def check_layer(expert_dtype="bf16", expert_path="big"):
 
 def main():
     print("device:", torch.cuda.get_device_name(0), flush=True)
-    for fn in (check_gate, check_ln, check_adam, check_layer, check_layer_small, check_layer_fp8):
+    selected = [a for a in sys.argv[1:] if not a.startswith("-")]
+    fns = (check_gate, check_ln, check_adam, check_layer, check_layer_small, check_layer_fp8)
+    if selected:   # e.g. under compute-sanitizer: python tools/gpu_layer_check.py check_layer check_layer_small
+        fns = [globals()[name] for name in selected]
+    for fn in fns:
         try:
             fn()
         except Exception as e:  # noqa
