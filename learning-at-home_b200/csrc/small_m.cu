@@ -391,11 +391,14 @@ wgrad_adam_kernel(const Params p, const __grid_constant__ CUtensorMap tmDY, cons
             mbar_init(&tmem_full[i], 1);
             mbar_init(&tmem_empty[i], 4);
         }
-        for (int i = 0; i < 4 * SLOTS; ++i) mbar_init(&st_full[i], 1);
         for (int i = 0; i < QD; ++i) {
             mbar_init(&q_full[i], 1);
             mbar_init(&q_empty[i], 5);   // MMA thread + 4 epilogue warps
         }
+        fence_mbar_init();
+    }
+    if (warp >= 2 && lane == 0) {   // every epilogue warp owns (initialises, arms, waits on) the barriers of its state ring
+        for (int i = 0; i < SLOTS; ++i) mbar_init(&st_full[(warp - 2) * SLOTS + i], 1);
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc(tmem_ptr, 2 * BN_MAX);

@@ -56,7 +56,8 @@ def _lib():
         "lah_adam_step": [P, P, P, P, P, P, I, P, I, P, P, I, Fl, Fl, Fl, Fl, Fl, I, I, I, L, P, Fl, I, P, L, I, I, I, P],
         "lah_bump_steps": [P, P, I, P],
         "lah_cast_bf16": [P, P, L, P],
-        "lah_attention_fwd": [P, P, I, I, I, P],
+        "lah_attention_fwd": [P, P, P, I, I, I, P],
+        "lah_attention_bwd": [P, P, P, P, P, P, I, I, I, P],
         "lah_symm_alloc": [c_ull, ctypes.POINTER(c_void_p)],
         "lah_symm_free": [P],
         "lah_symm_get_handle": [P, ctypes.c_char_p],
@@ -257,10 +258,11 @@ def gate_bwd(yo_off, grad, idx, pair_row, w, dlogits, k, E_loc, grid_size, route
 # ---------------------------------------------------------------------------------------------------------
 # attention (transformer expert)
 # ---------------------------------------------------------------------------------------------------------
-def attention_fwd(qkv, num_heads, *, out=None):
+def attention_fwd(qkv, num_heads, *, out=None, lse=None):
     """
     Self-attention over 512-token sequences on tcgen05 (csrc/attention.cu).
     :param qkv: [batch*512, 3*d_model] bf16 = in_proj output, [q | k | v] per token; head_dim must be 64
+    :param lse: optional fp32 [batch*512, num_heads]: receives the base-2 row log-sum-exp (needed by attention_bwd)
     :returns: [batch*512, d_model] bf16, heads concatenated (input of out_proj)
     """
     tokens, three_d = qkv.shape
@@ -268,10 +270,30 @@ def attention_fwd(qkv, num_heads, *, out=None):
     assert qkv.is_cuda and qkv.dtype == torch.bfloat16 and qkv.is_contiguous() and tokens % 512 == 0
     if out is None:
         out = torch.empty(tokens, d_model, dtype=torch.bfloat16, device=qkv.device)
-    native.check(_lib().lah_attention_fwd(ptr(qkv), ptr(out), tokens // 512, num_heads, d_model, stream_ptr()),
+    if lse is not None:
+        assert lse.dtype == torch.float32 and lse.is_contiguous() and lse.numel() == tokens * num_heads
+    native.check(_lib().lah_attention_fwd(ptr(qkv), ptr(out), ptr(lse), tokens // 512, num_heads, d_model, stream_ptr()),
                  "lah_attention_fwd")
     native.count_launch()
     return out
+
+
+def attention_bwd(qkv, out, dout, lse, num_heads):
+    """
+    Backward of ``attention_fwd`` on tcgen05 (csrc/attention_bwd.cu): recomputes P from the saved log-sum-exp, forms dV / dK /
+    dQ on tensor cores (nothing of size S x S touches HBM).  Returns dqkv [tokens, 3*d_model] bf16.
+    """
+    tokens, three_d = qkv.shape
+    d_model = three_d // 3
+    assert dout.dtype == torch.bfloat16 and dout.is_contiguous() and out.is_contiguous() and lse.dtype == torch.float32
+    delta = (dout.float() * out.float()).view(tokens, num_heads, d_model // num_heads).sum(-1).contiguous()
+    dqkv = torch.empty_like(qkv)
+    dq_acc = torch.zeros(tokens, d_model, dtype=torch.float32, device=qkv.device)
+    native.check(_lib().lah_attention_bwd(ptr(qkv), ptr(dout), ptr(lse), ptr(delta), ptr(dqkv), ptr(dq_acc), tokens // 512,
+                                          num_heads, d_model, stream_ptr()), "lah_attention_bwd")
+    native.count_launch()
+    dqkv[:, :d_model].copy_(dq_acc)
+    return dqkv
 
 
 def attention_ref(qkv, num_heads, seq_len=512):

@@ -72,7 +72,7 @@ class ExpertBackend(nn.Module):
 
     def forward(self, *inputs: torch.Tensor) -> Tuple[torch.Tensor, ...]:
         executor = self.native_executor(inputs)
-        if executor is not None and inputs[0].dim() == 2:
+        if executor is not None and inputs[0].dim() == executor.INPUT_DIMS:
             return (executor.forward(inputs[0]),)
         args, kwargs = nested_pack(inputs, structure=self.forward_schema)
         with torch.no_grad():
@@ -81,7 +81,7 @@ class ExpertBackend(nn.Module):
 
     def backward(self, *inputs: torch.Tensor) -> Tuple[torch.Tensor, ...]:
         executor = self.native_executor(inputs)
-        if executor is not None and len(inputs) == 2 and inputs[0].dim() == 2:
+        if executor is not None and len(inputs) == 2 and inputs[0].dim() == executor.INPUT_DIMS:
             grad_x = executor.backward(inputs[0], inputs[1].to(inputs[0].device))   # dgrad + fused wgrad/AMSGrad: one update
             self.update_count += 1
             return (grad_x,)

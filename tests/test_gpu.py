@@ -284,7 +284,8 @@ def test_rank_failure_is_detected_and_survivors_continue():
     assert out.returncode == 0 and "FAULT_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
 
 
-@pytest.mark.parametrize("check", ["check_attention", "check_layer", "check_ffn_native", "check_chain"])
+@pytest.mark.parametrize("check", ["check_attention", "check_attention_bwd", "check_layer", "check_transformer_train",
+                                   "check_ffn_native", "check_chain"])
 def test_attention_kernel_and_native_transformer_expert(check):
     """tcgen05 attention (csrc/attention.cu) and the sm_100a transformer expert vs fp32 PyTorch oracles"""
     from tools import gpu_attention_check as A

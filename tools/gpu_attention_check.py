@@ -53,6 +53,99 @@ def check_attention():
     print("attention_perf", results["attention_perf"], flush=True)
 
 
+def check_attention_bwd():
+    """tcgen05 attention backward (csrc/attention_bwd.cu) vs autograd through the fp32 reference attention"""
+    torch.manual_seed(3)
+    for batch, heads in [(1, 2), (2, 16)]:
+        d = heads * 64
+        qkv = (torch.randn(batch * 512, 3 * d, device="cuda") * 1.2).to(torch.bfloat16)
+        dout = torch.randn(batch * 512, d, device="cuda").to(torch.bfloat16)
+        lse = torch.empty(batch * 512, heads, device="cuda")
+        out = K.attention_fwd(qkv, heads, lse=lse)
+        dqkv = K.attention_bwd(qkv, out, dout, lse, heads)
+        torch.cuda.synchronize()
+        ref_in = qkv.float().requires_grad_(True)
+        K.attention_ref(ref_in, heads).backward(dout.float())
+        g = ref_in.grad
+        errs = dict(dq=rel(dqkv[:, :d], g[:, :d]), dk=rel(dqkv[:, d:2 * d], g[:, d:2 * d]), dv=rel(dqkv[:, 2 * d:], g[:, 2 * d:]))
+        # log-sum-exp emitted by the forward (base 2)
+        q, k, _ = qkv.float().view(batch, 512, 3, heads, 64).unbind(2)
+        s2 = torch.einsum("bqhd,bkhd->bhqk", q, k) * (0.125 * 1.4426950408889634)
+        lse_ref = torch.logsumexp(s2 * 0.6931471805599453, dim=-1) / 0.6931471805599453     # log2 sum 2^s
+        errs["lse"] = (lse.view(batch, 512, heads).transpose(1, 2) - lse_ref).abs().max().item()
+        results[f"attention_bwd_b{batch}_h{heads}"] = dict(ok=all(v < 3e-2 for v in errs.values()), **errs)
+        print(f"attention_bwd_b{batch}_h{heads}", results[f"attention_bwd_b{batch}_h{heads}"], flush=True)
+    batch, heads, d = 32, 16, 1024
+    qkv = torch.randn(batch * 512, 3 * d, device="cuda").to(torch.bfloat16)
+    dout = torch.randn(batch * 512, d, device="cuda").to(torch.bfloat16)
+    lse = torch.empty(batch * 512, heads, device="cuda")
+    out = K.attention_fwd(qkv, heads, lse=lse)
+    ms = timeit(lambda: K.attention_bwd(qkv, out, dout, lse, heads))
+    flops = 10.0 * batch * heads * 512 * 512 * 64
+    q4 = qkv.view(batch, 512, 3, heads, 64)
+    q, k, v = (q4[:, :, i].transpose(1, 2).detach().requires_grad_(True) for i in range(3))
+    o = torch.nn.functional.scaled_dot_product_attention(q, k, v)
+    go = dout.view(batch, 512, heads, 64).transpose(1, 2)
+    ms_sdpa = timeit(lambda: torch.autograd.grad(o, (q, k, v), go, retain_graph=True))
+    results["attention_bwd_perf"] = dict(ok=True, ms=ms, tflops=flops / ms / 1e9, sdpa_bwd_ms=ms_sdpa)
+    print("attention_bwd_perf", results["attention_bwd_perf"], flush=True)
+
+
+def check_transformer_train():
+    """the TRAINABLE sm_100a transformer expert (ExpertBackend + NativeTransformerExecutor): forward, input gradients and three
+    AMSGrad steps against the fp32 nn.Module + torch.optim.Adam"""
+    import copy
+    import lah_b200 as lib
+    torch.manual_seed(4)
+    layer = TransformerEncoderLayer(1024, 16, dropout=0.0).cuda()
+    ref = copy.deepcopy(layer)
+    ref_opt = torch.optim.Adam(ref.parameters(), lr=1e-4, amsgrad=True)
+    be = lib.ExpertBackend(name="t", expert=layer, opt=torch.optim.Adam(layer.parameters(), lr=1e-4, amsgrad=True),
+                           args_schema=(lib.BatchTensorProto(512, 1024),), outputs_schema=lib.BatchTensorProto(512, 1024),
+                           max_batch_size=8)
+    x = torch.randn(2, 512, 1024, device="cuda")
+    g = torch.randn(2, 512, 1024, device="cuda") * 0.1
+    (y,) = be.forward(x)
+    native_used = type(be._executor).__name__ == "NativeTransformerExecutor"
+    errs = dict(fwd=rel(y, ref(x)))
+    for it in range(3):
+        (gx,) = be.backward(x, g)
+        xr = x.clone().requires_grad_(True)
+        ref(xr).backward(g)
+        if it == 0:
+            errs["dx"] = rel(gx, xr.grad)
+            # VALUE of the weight gradients: first Adam step -> exp_avg = 0.1 * grad
+            st = be.opt.state_dict()["state"]
+            names = [n for n, _ in ref.named_parameters()]
+            for i, (n, p) in enumerate(ref.named_parameters()):
+                if n in ("self_attn.in_proj_weight", "linear1.weight", "linear2.weight", "self_attn.out_proj.weight",
+                         "self_attn.in_proj_bias", "norm1.weight"):
+                    errs["g_" + n] = rel(st[i]["exp_avg"] / 0.1, p.grad)
+        ref_opt.step(), ref_opt.zero_grad()
+    sd, rsd = be.state_dict(), ref.state_dict()
+    errs["param_mean_abs_diff"] = max((sd["expert." + k] - v).abs().mean().item() for k, v in rsd.items())
+    ok = native_used and errs["fwd"] < 3e-2 and errs["dx"] < 5e-2 and errs["param_mean_abs_diff"] < 5e-5 and \
+        all(v < 6e-2 for k, v in errs.items() if k.startswith("g_"))
+    results["transformer_train"] = dict(ok=bool(ok), native=native_used, **errs)
+    print("transformer_train", results["transformer_train"], flush=True)
+    xb = torch.randn(8, 512, 1024, device="cuda")
+    gb = torch.randn(8, 512, 1024, device="cuda") * 0.1
+    ms = timeit(lambda: be.backward(xb, gb), iters=5)
+    ref_bf = copy.deepcopy(ref)
+
+    def torch_step():
+        xr = xb.clone().requires_grad_(True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            out = ref_bf(xr)
+        out.backward(gb)
+        ref_opt_bf.step(), ref_opt_bf.zero_grad()
+
+    ref_opt_bf = torch.optim.Adam(ref_bf.parameters(), lr=1e-4, amsgrad=True, fused=True)
+    ms_t = timeit(torch_step, iters=5)
+    results["transformer_train_perf"] = dict(ok=True, ms_fwd_bwd_adam_8seq=ms, torch_bf16_autocast_ms=ms_t, seqs_per_s=8 / ms * 1e3)
+    print("transformer_train_perf", results["transformer_train_perf"], flush=True)
+
+
 def check_layer():
     torch.manual_seed(1)
     layer = TransformerEncoderLayer(1024, 16).cuda().eval()
@@ -118,7 +211,7 @@ def check_chain():
 
 
 if __name__ == "__main__":
-    for fn in (check_attention, check_layer, check_ffn_native, check_chain):
+    for fn in (check_attention, check_attention_bwd, check_layer, check_transformer_train, check_ffn_native, check_chain):
         try:
             fn()
         except Exception as e:  # noqa
