@@ -8,7 +8,7 @@
 //     S   = Q_i K_j^T                 (128 x 128)        dP  = dO_i V_j^T              (128 x 128)
 //     P   = exp2(S * scale*log2e - LSE_i)   [recomputed from the forward's row log-sum-exp: no second softmax pass]
 //     dS  = P o (dP - Delta_i) * scale      [Delta = rowsum(dO o O)]
-//     dV_j += P^T dO_i   (128 x 64)    dK_j += dS^T Q_i  (128 x 64)    dQ_i = dS K_j  (128 x 64, accumulated over j with red.add)
+//     dV_j += P^T dO_i   (128 x 64)    dK_j += dS^T Q_i  (128 x 64)    dQ_i^(j) = dS K_j  (128 x 64, one partial per key block j)
 //
 // P and dS are written ONCE to shared memory (bf16, 128B-swizzled [query rows][64 keys] atoms) and consumed three ways by
 // tcgen05.mma without any transpose: as an MN-major A operand (P^T, dS^T) and as a K-major A operand (dS); Q_i, dO_i, K_j are
@@ -43,7 +43,8 @@ constexpr int COL_S = 0, COL_DP = 128, COL_DV = 256, COL_DK = 320, COL_DQ = 384;
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
                      const float* __restrict__ lse2, const float* __restrict__ delta, bf16* __restrict__ dqkv,
-                     float* __restrict__ dq_acc, int d_model, int num_heads, float scale, float scale_log2e) {
+                     float* __restrict__ dq_part, long long total_tokens, int d_model, int num_heads, float scale,
+                     float scale_log2e) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
@@ -180,14 +181,18 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
             mbar_arrive(p_full);
             mbar_wait(dq_full, i & 1);
             tcgen05_fence_after();
-            float* dq = dq_acc + token * d_model + head * HEAD_DIM;
+            // partial dQ of THIS key block: plain 16 B stores of the thread's 256 contiguous bytes into slice j of dq_part
+            // ([4, T, D] fp32; the caller sums the four slices while casting to bf16) — no atomics
+            float4* dq = reinterpret_cast<float4*>(dq_part + (static_cast<long long>(j) * total_tokens + token) * d_model + head * HEAD_DIM);
 #pragma unroll 1
             for (int c = 0; c < HEAD_DIM / 32; ++c) {
                 uint32_t r[32];
                 tmem_ld_32x32(lane_base + COL_DQ + c * 32, r);
                 tmem_ld_wait();
 #pragma unroll
-                for (int e = 0; e < 32; ++e) atomicAdd(dq + c * 32 + e, __uint_as_float(r[e]));   // 4 key blocks meet here
+                for (int e = 0; e < 8; ++e)
+                    dq[c * 8 + e] = make_float4(__uint_as_float(r[4 * e]), __uint_as_float(r[4 * e + 1]), __uint_as_float(r[4 * e + 2]),
+                                                __uint_as_float(r[4 * e + 3]));
             }
             tcgen05_fence_before();
         }
@@ -238,8 +243,8 @@ using namespace lah::attnb;
 extern "C" {
 
 // qkv [T, 3D] bf16 (forward input), dout [T, D] bf16, lse2 [T, H] fp32 (forward output), delta [T, H] fp32 = rowsum(dout o out)
-// -> dqkv [T, 3D] bf16: the K and V thirds are written here; dq_acc [T, D] fp32 (ZEROED by the caller) receives dQ
-int lah_attention_bwd(const void* qkv, const void* dout, const float* lse2, const float* delta, void* dqkv, float* dq_acc,
+// -> dqkv [T, 3D] bf16: the K and V thirds are written here; dq_part [4, T, D] fp32 receives the four per-key-block partials of dQ
+int lah_attention_bwd(const void* qkv, const void* dout, const float* lse2, const float* delta, void* dqkv, float* dq_part,
                       int batch, int num_heads, int d_model, cudaStream_t st) {
     if (d_model != num_heads * HEAD_DIM) return -2;
     static PFN_encodeTiled fn = nullptr;
@@ -278,7 +283,8 @@ int lah_attention_bwd(const void* qkv, const void* dout, const float* lse2, cons
     if (batch <= 0) return 0;
     const float scale = 1.f / sqrtf((float)HEAD_DIM);
     attention_bwd_kernel<<<batch * num_heads * (S_LEN / BLK), NUM_THREADS, SMEM_TOTAL, st>>>(
-        tm_qkv, tm_do, lse2, delta, (bf16*)dqkv, dq_acc, d_model, num_heads, scale, scale * 1.4426950408889634f);
+        tm_qkv, tm_do, lse2, delta, (bf16*)dqkv, dq_part, (long long)batch * S_LEN, d_model, num_heads, scale,
+        scale * 1.4426950408889634f);
     return -(int)cudaGetLastError();
 }
 

@@ -288,11 +288,11 @@ def attention_bwd(qkv, out, dout, lse, num_heads):
     assert dout.dtype == torch.bfloat16 and dout.is_contiguous() and out.is_contiguous() and lse.dtype == torch.float32
     delta = (dout.float() * out.float()).view(tokens, num_heads, d_model // num_heads).sum(-1).contiguous()
     dqkv = torch.empty_like(qkv)
-    dq_acc = torch.zeros(tokens, d_model, dtype=torch.float32, device=qkv.device)
-    native.check(_lib().lah_attention_bwd(ptr(qkv), ptr(dout), ptr(lse), ptr(delta), ptr(dqkv), ptr(dq_acc), tokens // 512,
+    dq_part = torch.empty(4, tokens, d_model, dtype=torch.float32, device=qkv.device)   # one partial per 128-key block
+    native.check(_lib().lah_attention_bwd(ptr(qkv), ptr(dout), ptr(lse), ptr(delta), ptr(dqkv), ptr(dq_part), tokens // 512,
                                           num_heads, d_model, stream_ptr()), "lah_attention_bwd")
     native.count_launch()
-    dqkv[:, :d_model].copy_(dq_acc)
+    dqkv[:, :d_model].copy_(dq_part.sum(0))
     return dqkv
 
 
