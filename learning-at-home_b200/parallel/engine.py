@@ -73,7 +73,9 @@ class DMoEConfig:
     #   "small": the reference's operating point (64 trainers x batch 4 => O(16) rows per expert): swap-AB tcgen05 tiles
     #            that stream every weight once (small_m.cu), groups padded to 16 rows, weight gradient + AMSGrad fused in
     #            one kernel (the gradient never reaches HBM)
-    #   "auto":  "small" when a step brings fewer than 128 rows per expert on average
+    #   "auto":  "small" when a step brings fewer than 512 rows per expert on average (up to there streaming the weights
+    #            through 128-token swap-AB tiles, with the fused optimizer and the step in one CUDA graph, beats padding every
+    #            expert to 256-row CTA-pair tiles; beyond, the 2x more efficient pair tiles win)
     expert_path: str = "auto"
     # asynchronous expert updates (reference: EmulatedDMoE.update_every_inputs / update_every_steps,
     # experiments/convergence/dmoe_emulator.py:70-77): an expert accumulates weight gradients and steps once it has seen
@@ -95,7 +97,7 @@ class DMoEConfig:
         if self.expert_path != "auto":
             return self.expert_path
         rows_per_expert = self.tokens_per_rank * world * self.k / max(1, self.num_experts)
-        return "small" if (rows_per_expert < 128 and self.expert_dtype == "bf16" and self.inner % 128 == 0
+        return "small" if (rows_per_expert < 512 and self.expert_dtype == "bf16" and self.inner % 128 == 0
                            and self.hidden % 128 == 0) else "big"
 
     @property

@@ -65,7 +65,10 @@ class DMoETrainer:
         self.model = DMoEClassifier(cfg, self.ctx, device=self.device).to(self.device)
         self._flatten_trainer_params()
         self.step_count = 0
-        self.use_graph = bool(self.cuda and (self.ctx.small if use_graph is None else use_graph))
+        # automatic: whenever a step is short enough to be launch-bound (always on the small path; on the big path up to a few
+        # thousand rows per rank)
+        auto = self.cuda and (self.ctx.small or cfg.tokens_per_rank <= 4096)
+        self.use_graph = bool(self.cuda and (auto if use_graph is None else use_graph))
         self._graph, self._graph_B, self._eager_steps = None, -1, 0
         B = cfg.tokens_per_rank
         if self.cuda:

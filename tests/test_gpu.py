@@ -77,21 +77,22 @@ def test_small_m_kernels(check):
     assert S.results and not bad, bad
 
 
-def test_cuda_graph_step_equals_eager_step():
+@pytest.mark.parametrize("path", ["small", "big"])
+def test_cuda_graph_step_equals_eager_step(path):
     """the whole training step captured in ONE CUDA graph (device-side epochs / step counters) == the eager step"""
     import lah_b200  # noqa
     from lah_b200.ops import native
     from lah_b200.parallel import engine as E
     from lah_b200.parallel.trainer import DMoETrainer
     cfg = E.DMoEConfig(hidden=512, grid_size=(16,), k=4, num_layers=2, tokens_per_rank=256, gate_mode="emulator", failure_rate=0.1,
-                       lr=1e-4)   # small steps: atomics-order noise must not be amplified by the optimisation itself
+                       lr=1e-4, expert_path=path)   # small lr: atomics-order noise must not be amplified by the optimisation
     torch.manual_seed(0)
     xs = [torch.randn(256, cfg.in_features, device="cuda") for _ in range(6)]
     ys = [torch.randint(0, 10, (256,), device="cuda") for _ in range(6)]
     losses = {}
     for graph in (False, True):
         t = DMoETrainer(cfg, use_graph=graph)
-        assert t.ctx.small
+        assert t.ctx.small == (path == "small")
         losses[graph] = [float(t.train_step_device(x, y)) for x, y in zip(xs, ys)]
         if graph:
             assert t._graph is not None and t._graph_launches > 20 and native.launches() > 0
@@ -264,7 +265,7 @@ def test_fused_trainer_matches_baseline_trainer_one_step():
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("extra", [[], ["--force-shadow"]])
+@pytest.mark.parametrize("extra", [[], ["--force-shadow"], ["--small"]])
 def test_two_gpu_p2p_dispatch_matches_single_gpu(extra):
     """fused P2P engine on 2 GPUs == single-process oracle; with --force-shadow the hot-expert replica path (weights pulled
     over NVLink, partial weight gradients reduced inside the owner's Adam kernel) is exercised for 4 experts"""
