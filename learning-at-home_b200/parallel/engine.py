@@ -77,6 +77,11 @@ class DMoEConfig:
     #            through 128-token swap-AB tiles, with the fused optimizer and the step in one CUDA graph, beats padding every
     #            expert to 256-row CTA-pair tiles; beyond, the 2x more efficient pair tiles win)
     expert_path: str = "auto"
+    # small path: run the fused weight-gradient + AMSGrad kernels (bandwidth-bound, ~75 % of the step) on a SECOND stream,
+    # concurrently with the latency-bound chain of the backward pass (dgrads, LayerNorm backward, combine, the next layer's
+    # dispatch).  `optimizer_ctas` SMs stream optimizer state, the chain keeps the remaining ones (persistent kernels of both
+    # sides are launched with matching CTA limits so that neither starves the other).  0 disables the overlap.
+    optimizer_ctas: int = 96
     # asynchronous expert updates (reference: EmulatedDMoE.update_every_inputs / update_every_steps,
     # experiments/convergence/dmoe_emulator.py:70-77): an expert accumulates weight gradients and steps once it has seen
     # >= update_every_inputs rows or >= update_every_steps steps since its first pending row.  (0, 0) = step after every
@@ -165,7 +170,7 @@ class EngineContext:
         self.max_tiles = self.max_rows // self.tile_rows
         H = cfg.hidden
         sym_rows_bytes = self.max_rows * H * 2
-        need = (2 * cfg.num_layers + 2) * (sym_rows_bytes + 4096) + K.MAX_WORLD * self.E * 4 + (32 << 20)
+        need = (3 * cfg.num_layers + 2) * (sym_rows_bytes + 4096) + K.MAX_WORLD * self.E * 4 + (32 << 20)
         if self.S:  # parameters, bf16 mirror and gradients of the shards are peer-visible (replica pull / gradient reduce)
             rec = sum(int(math.prod(shape)) for shape in cfg.seg_shapes().values())
             need += cfg.num_layers * (self.G_tot * rec * 10 + (1 << 20))
@@ -188,6 +193,13 @@ class EngineContext:
         K.set_spin_timeout_ms(cfg.peer_timeout_ms)
         self.step_ctr[1] = int(cfg.peer_timeout_ms)   # the GEMM producers read the timeout from the same device words
         self.dead_mask = 0                            # ranks excluded from every flag wait / reduce (host-decided)
+        import os as _os
+        octas = int(_os.environ.get("LAH_OPTIMIZER_CTAS", cfg.optimizer_ctas))
+        sms = torch.cuda.get_device_properties(self.device).multi_processor_count
+        self.opt_ctas = octas if (self.small and 0 < octas < sms - 8) else 0     # CTAs of the optimizer stream (0: no overlap)
+        self.chain_ctas = sms - self.opt_ctas if self.opt_ctas else 0            # CTA limit of the persistent chain kernels
+        self.opt_stream = torch.cuda.Stream(self.device) if self.opt_ctas else None
+        self._opt_pending = False
         K.set_poison_word(self.status)   # a step in which a peer timed out applies no optimizer update (the batch fails)
         assert 2 * cfg.num_layers + 4 < self.EPOCH_STRIDE
         self.alive = torch.ones(self.E, dtype=torch.uint8, device=self.device)
@@ -288,6 +300,13 @@ class EngineContext:
         hb = self.hb.cpu().double()
         now_ms = (time.time() if now is None else now) * 1000
         return torch.where(hb > 0, (now_ms - hb) / 1000.0, torch.full_like(hb, float("inf")))
+
+    def join_optimizer_stream(self):
+        """the launching stream waits for the fused wgrad+AMSGrad kernels of this step (they run on `opt_stream`); called once
+        per step before anything may read the updated weights.  Inside a CUDA-graph capture this is a graph edge."""
+        if self.opt_stream is not None and self._opt_pending:
+            torch.cuda.current_stream(self.device).wait_stream(self.opt_stream)
+            self._opt_pending = False
 
     def begin_step(self):
         """advance the device-side epoch / token bases (one tiny kernel) and restart the step-relative counters; called at
@@ -494,6 +513,13 @@ class LayerWorkspace:
         self.tile_group = torch.full((ctx.max_tiles,), -1, **i32)
         self.total_rows = torch.zeros(1, **i32)
         self.outstanding = False   # a training-mode forward whose backward has not run yet owns this workspace
+        # small path with optimizer overlap: the fused wgrad+AMSGrad kernels of layer L read dY buffers while the main stream is
+        # already in the backward of layer L-1, so they must be per layer (a few MB each at this batch size)
+        if ctx.small and ctx.opt_stream is not None:
+            self.gyd, self.gyd_off = ctx.heap.alloc((R, H), torch.bfloat16)
+            self.dh2, self.dh1 = torch.zeros(R, I, **bf), torch.zeros(R, I, **bf)
+        else:
+            self.gyd, self.gyd_off, self.dh2, self.dh1 = ctx.gyd, ctx.gyd_off, ctx.dh, ctx.dh
 
 
 # =========================================================================================================
@@ -562,10 +588,19 @@ class FusedDMoE(nn.Module):
         if self.cfg.gate_mode == "emulator" and proj is None:
             if x.is_cuda and x.dtype == torch.bfloat16:
                 # trainer-side gate on the activation dtype: one bf16 LayerNorm + one small tensor-core GEMM instead of
-                # fp32 casts of the whole [B, H] activation (4 % of the step); accumulation stays fp32 inside the ops
+                # fp32 casts of the whole [B, H] activation (4 % of the step); accumulation stays fp32 inside the ops.
+                # The gate parameters are frozen (like the reference emulator's): their bf16 / normalised forms are cached
+                # (keyed on the tensors' version counters), which removes four small kernels per layer and step
                 ln = self.gating_pre_normalize
-                xn = F.layer_norm(x, (x.shape[-1],), ln.weight.to(x.dtype), ln.bias.to(x.dtype), ln.eps)
-                return (xn @ F.normalize(self.expert_keys, dim=-1).to(x.dtype)).float()
+                key = (self.expert_keys._version, ln.weight._version, ln.bias._version, self.expert_keys.data_ptr())
+                if getattr(self, "_gate_cache_key", None) != key:
+                    with torch.no_grad():
+                        self._gate_cache = (ln.weight.to(x.dtype), ln.bias.to(x.dtype),
+                                            F.normalize(self.expert_keys, dim=-1).to(x.dtype).contiguous())
+                    self._gate_cache_key = key
+                w_ln, b_ln, keys = self._gate_cache
+                xn = F.layer_norm(x, (x.shape[-1],), w_ln, b_ln, ln.eps)
+                return (xn @ keys).float()
             return self.gating_pre_normalize(x.float()) @ F.normalize(self.expert_keys, dim=-1)
         return F.linear(x.float(), proj.weight, proj.bias)
 
@@ -588,6 +623,7 @@ class FusedDMoE(nn.Module):
         c, ws, sh, cfg = self.ctx, self.ws, self.shard, self.cfg
         B, k = x.shape[0], cfg.k
         P = B * k
+        c.join_optimizer_stream()   # no-op inside DMoETrainer steps (joined there); protects layer-level callers
         epoch = c.next_epoch()
         idx, w, pos, pair_row = ws.idx[:P], ws.w[:P], ws.pos[:P], ws.pair_row[:P]
         K.gate_topk(logits, self.grid_size, k, alive=c.alive, failure_rate=cfg.failure_rate if self.training else 0.0,
@@ -662,7 +698,7 @@ class FusedDMoE(nn.Module):
         gy = gy.to(torch.bfloat16)
         dlogits = torch.empty(B, sum(self.grid_size), dtype=torch.float32, device=gy.device)
         K.gate_bwd(ws.yo_off, gy, idx, pair_row, w, dlogits, k, c.E_loc, self.grid_size, route_owner=ws.route_owner)
-        K.scatter_rows(gy, w, idx, pos, None, pair_row, c.gyd_off, c.flags_off, K.SLOT_GRAD, epoch, k, c.E_loc,
+        K.scatter_rows(gy, w, idx, pos, None, pair_row, ws.gyd_off, c.flags_off, K.SLOT_GRAD, epoch, k, c.E_loc,
                        c.max_rows, ws.group_off, ws.group_rows, c.done_counter, c.status, align=c.align,
                        route_owner=ws.route_owner, num_groups=c.G_tot)
         if c.S:  # atomically accumulated (bias / LayerNorm) partial gradients of my shadow slots start from zero
@@ -712,24 +748,36 @@ class FusedDMoE(nn.Module):
         tg, go, rows, T = ws.tile_group, ws.group_off, ws.group_rows, c.tile_rows
         gr = sh.grads
         opt = dict(lr=cfg.lr, betas=cfg.betas, eps=cfg.eps, amsgrad=cfg.amsgrad)
+        main = torch.cuda.current_stream(c.device)
+        side, chain_ctas = c.opt_stream, c.chain_ctas
 
-        def wgrad(name, dy, x):   # dW never reaches HBM: TMEM accumulator -> AMSGrad epilogue -> TMA stores of p / m / v / vmax
-            K.wgrad_adam(dy, x, go, rows, p=sh.views[name][:self.E_loc], m=sh.m_views[name][:self.E_loc],
-                         v=sh.v_views[name][:self.E_loc], vmax=sh.vmax_views[name][:self.E_loc] if cfg.amsgrad else None,
-                         p_bf16=sh.bf16[name], step=sh.step, **opt)
+        def wgrad(name, dy, x):
+            """dW never reaches HBM: TMEM accumulator -> AMSGrad epilogue -> TMA stores of p / m / v / vmax.  With the overlap
+            enabled the kernel goes to the optimizer stream, ordered after everything the main stream has launched so far (in
+            particular the dgrad that still reads the OLD weights); its inputs live in per-layer buffers."""
+            kw = dict(p=sh.views[name][:self.E_loc], m=sh.m_views[name][:self.E_loc], v=sh.v_views[name][:self.E_loc],
+                      vmax=sh.vmax_views[name][:self.E_loc] if cfg.amsgrad else None, p_bf16=sh.bf16[name], step=sh.step, **opt)
+            if side is None:
+                K.wgrad_adam(dy, x, go, rows, **kw)
+                return
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                K.wgrad_adam(dy, x, go, rows, max_ctas=c.opt_ctas, **kw)
+            c._opt_pending = True
 
+        gyd, dh2, dh1 = ws.gyd, ws.dh2, ws.dh1
         K.bump_steps(sh.step, ws.step_rows)
-        K.grouped_colsum(c.gyd, tg, out=gr["b3"], tile_rows=T)
-        K.swapab_linear(c.gyd, sh.bf16["w3"], go, rows, out=c.da, w_is_kn=True)
-        wgrad("w3", c.gyd, ws.a2)
-        K.ln_relu_bwd(c.da, ws.h2, ws.mean2, ws.rstd2, sh.views["g2"], sh.views["be2"], tg, dh=c.dh, dgamma=gr["g2"],
+        K.grouped_colsum(gyd, tg, out=gr["b3"], tile_rows=T)
+        K.swapab_linear(gyd, sh.bf16["w3"], go, rows, out=c.da, w_is_kn=True, max_ctas=chain_ctas)
+        wgrad("w3", gyd, ws.a2)
+        K.ln_relu_bwd(c.da, ws.h2, ws.mean2, ws.rstd2, sh.views["g2"], sh.views["be2"], tg, dh=dh2, dgamma=gr["g2"],
                       dbeta=gr["be2"], dbias=gr["b2"], tile_rows=T)
-        K.swapab_linear(c.dh, sh.bf16["w2"], go, rows, out=c.da, w_is_kn=True)
-        wgrad("w2", c.dh, ws.a1)
-        K.ln_relu_bwd(c.da, ws.h1, ws.mean1, ws.rstd1, sh.views["g1"], sh.views["be1"], tg, dh=c.dh, dgamma=gr["g1"],
+        K.swapab_linear(dh2, sh.bf16["w2"], go, rows, out=c.da, w_is_kn=True, max_ctas=chain_ctas)
+        wgrad("w2", dh2, ws.a1)
+        K.ln_relu_bwd(c.da, ws.h1, ws.mean1, ws.rstd1, sh.views["g1"], sh.views["be1"], tg, dh=dh1, dgamma=gr["g1"],
                       dbeta=gr["be1"], dbias=gr["b1"], tile_rows=T)
-        K.swapab_linear(c.dh, sh.bf16["w1"], go, rows, out=c.dxd, w_is_kn=True, residual=c.gyd)
-        wgrad("w1", c.dh, ws.xd)
+        K.swapab_linear(dh1, sh.bf16["w1"], go, rows, out=c.dxd, w_is_kn=True, residual=gyd, max_ctas=chain_ctas)
+        wgrad("w1", dh1, ws.xd)
         # biases / LayerNorm affine: the ordinary fused AMSGrad restricted to the small segments
         K.adam_step(sh.p, sh.g, sh.m, sh.v, sh.vmax, sh.p_bf16, sh.seg_sizes, sh.slots, step=sh.step,
                     group_rows=ws.step_rows, zero_mask=SMALL_SEG_MASK, G_active=self.E_loc, seg_mask=SMALL_SEG_MASK, **opt)

@@ -225,6 +225,8 @@ class DMoETrainer:
         if not self.cuda:
             for block in self.model.blocks:
                 block.apply_expert_gradients_ref()
+        if self.cuda:
+            self.ctx.join_optimizer_stream()   # the expert optimizers of this step (second stream) complete inside the step
         if timer is not None:
             timer.mark("trainer_bwd(stem+gates)")
         if self._stale_ring is not None:
@@ -417,3 +419,4 @@ class DMoETrainer:
                     block.shard.load_expert_optimizer_state(le, state["experts"][uid]["optimizer"])
         if "rng" in state:
             torch.set_rng_state(state["rng"])
+        self._graph, self._eager_steps = None, 0   # cached derived tensors (bf16 gate keys, ...) are rebuilt eagerly first
