@@ -80,8 +80,10 @@ class DMoEConfig:
     # small path: run the fused weight-gradient + AMSGrad kernels (bandwidth-bound, ~75 % of the step) on a SECOND stream,
     # concurrently with the latency-bound chain of the backward pass (dgrads, LayerNorm backward, combine, the next layer's
     # dispatch).  `optimizer_ctas` SMs stream optimizer state, the chain keeps the remaining ones (persistent kernels of both
-    # sides are launched with matching CTA limits so that neither starves the other).  0 disables the overlap.
-    optimizer_ctas: int = 96
+    # sides are launched with matching CTA limits so that neither starves the other).  0 disables the overlap, -1 = automatic:
+    # 116 of 148 on one GPU, 96 when the experts are sharded (measured: 1 GPU 10.96 -> 10.06 ms, 2 GPUs 7.08 -> 6.54 ms,
+    # 4 GPUs 5.16 -> 4.32 ms per step; 64 and >= 132 are slower than no overlap — profiles/overlap_sweep_r2.md)
+    optimizer_ctas: int = -1
     # asynchronous expert updates (reference: EmulatedDMoE.update_every_inputs / update_every_steps,
     # experiments/convergence/dmoe_emulator.py:70-77): an expert accumulates weight gradients and steps once it has seen
     # >= update_every_inputs rows or >= update_every_steps steps since its first pending row.  (0, 0) = step after every
@@ -195,6 +197,8 @@ class EngineContext:
         self.dead_mask = 0                            # ranks excluded from every flag wait / reduce (host-decided)
         import os as _os
         octas = int(_os.environ.get("LAH_OPTIMIZER_CTAS", cfg.optimizer_ctas))
+        if octas < 0:
+            octas = 116 if self.world == 1 else 96
         sms = torch.cuda.get_device_properties(self.device).multi_processor_count
         self.opt_ctas = octas if (self.small and 0 < octas < sms - 8) else 0     # CTAs of the optimizer stream (0: no overlap)
         self.chain_ctas = sms - self.opt_ctas if self.opt_ctas else 0            # CTA limit of the persistent chain kernels
