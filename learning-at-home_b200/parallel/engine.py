@@ -94,6 +94,10 @@ class DMoEConfig:
     # sleeps delay_ms and applies them `delay_steps` updates later): the trainer-side optimizer applies the gradient computed
     # `trainer_staleness` steps ago; experts keep updating themselves immediately, exactly like the reference
     trainer_staleness: int = 0
+    # trainers per rank and step: the batch is split into this many micro-batches processed one after the other; the experts
+    # step after EVERY micro-batch's backward (per-backward-batch updates of lib/runtime/expert_backend.py:90-97), the trainer
+    # parameters once per step
+    trainer_microbatches: int = 1
     # peer-flag wait timeout in ms (0 = ~10 s).  On expiry the waiting rank marks the step degraded (status bit) and goes on
     # with whatever arrived — the fused-path analogue of run_and_await_k's timeout_after_k_min (lib/utils/threading.py:76-125)
     peer_timeout_ms: int = 0

@@ -217,16 +217,35 @@ class DMoETrainer:
             self.ctx.begin_step()
         if timer is not None:
             timer.start()
-        logits = self.model(x)
-        loss = F.cross_entropy(logits.float(), y)
-        if timer is not None:
-            timer.mark("head+loss")
-        loss.backward()  # expert updates happen inside (server-side semantics), trainer grads land in flat_g
-        if not self.cuda:
-            for block in self.model.blocks:
-                block.apply_expert_gradients_ref()
-        if self.cuda:
-            self.ctx.join_optimizer_stream()   # the expert optimizers of this step (second stream) complete inside the step
+        m = max(1, int(self.cfg.trainer_microbatches))
+        if m == 1:
+            logits = self.model(x)
+            loss = F.cross_entropy(logits.float(), y)
+            if timer is not None:
+                timer.mark("head+loss")
+            loss.backward()  # expert updates happen inside (server-side semantics), trainer grads land in flat_g
+            if not self.cuda:
+                for block in self.model.blocks:
+                    block.apply_expert_gradients_ref()
+            if self.cuda:
+                self.ctx.join_optimizer_stream()   # the expert optimizers of this step (second stream) complete inside the step
+        else:
+            # several trainers per rank (reference: num_trainers threads, each with its own small batch): the batch is processed
+            # as m micro-batches ONE AFTER THE OTHER; every micro-batch's backward steps the experts it used (so later trainers
+            # of the same step already see the updated experts, like concurrent trainers of the reference do), while the
+            # trainer-side gradients are averaged over the micro-batches and applied once (optionally stale)
+            assert x.shape[0] % m == 0, "trainer_microbatches must divide the batch"
+            total = None
+            for xm, ym in zip(x.chunk(m), y.chunk(m)):
+                loss_m = F.cross_entropy(self.model(xm).float(), ym) / m
+                loss_m.backward()
+                if not self.cuda:
+                    for block in self.model.blocks:
+                        block.apply_expert_gradients_ref()
+                else:
+                    self.ctx.join_optimizer_stream()
+                total = loss_m.detach() if total is None else total + loss_m.detach()
+            loss = total
         if timer is not None:
             timer.mark("trainer_bwd(stem+gates)")
         if self._stale_ring is not None:

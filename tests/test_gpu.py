@@ -121,6 +121,21 @@ def test_update_every_inputs_accumulates_like_the_emulator():
     t.close()
 
 
+def test_trainer_microbatches_on_gpu():
+    """several trainers per rank: experts step after every micro-batch's backward, the trainer once per step (graph-captured)"""
+    import lah_b200  # noqa
+    from lah_b200.parallel import engine as E
+    from lah_b200.parallel.trainer import DMoETrainer
+    cfg = E.DMoEConfig(hidden=512, grid_size=(4, 4), k=4, num_layers=2, tokens_per_rank=256, trainer_microbatches=2, trainer_staleness=1)
+    t = DMoETrainer(cfg)
+    x, y = torch.randn(256, cfg.in_features, device="cuda"), torch.randint(0, 10, (256,), device="cuda")
+    losses = [float(t.train_step_device(x, y)) for _ in range(6)]
+    t.ctx.check_status()
+    assert int(t.model.blocks[0].shard.step.max()) == 12 and t._graph is not None
+    assert losses[-1] < losses[0]
+    t.close()
+
+
 def test_public_api_runs_the_engine():
     """README-style code (lib.GatingFunction over a network) on CUDA tensors runs the sm_100a layer:
     InBoxNetwork.bind_engine -> GatingFunction.forward -> FusedDMoE.forward_with_gate; heartbeats reach the gate kernel

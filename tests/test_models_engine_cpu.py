@@ -314,3 +314,26 @@ def test_stale_trainer_gradients_and_update_every_on_cpu():
     assert not torch.equal(tr.model.head.weight, w0)      # ... the gradient of step 0 arrives with step 2
     losses = [tr.train_step(x, y) for _ in range(40)]
     assert losses[-1] < 0.7 * losses[0]
+
+
+def test_expert_path_selection():
+    """"small" (swap-AB weight streaming, fused wgrad+AMSGrad) below 512 rows per expert and step, "big" (CTA-pair tiles) above;
+    gradient accumulation and FP8 forward GEMMs live on the big path"""
+    named = E.DMoEConfig(hidden=512, grid_size=(64,), k=4, tokens_per_rank=256)
+    assert named.resolved_path(1) == "small" and named.resolved_path(8) == "small"      # 16 .. 128 rows per expert
+    assert E.DMoEConfig(hidden=512, grid_size=(64,), k=4, tokens_per_rank=65536).resolved_path(1) == "big"
+    assert E.DMoEConfig(hidden=512, grid_size=(64,), k=4, tokens_per_rank=256, update_every_steps=3).resolved_path(1) == "big"
+    assert E.DMoEConfig(hidden=512, grid_size=(64,), k=4, tokens_per_rank=256, expert_dtype="fp8").resolved_path(1) == "big"
+    assert E.DMoEConfig(hidden=512, grid_size=(64,), k=4, tokens_per_rank=256, expert_path="big").resolved_path(1) == "big"
+
+
+def test_trainer_microbatches_step_experts_per_microbatch():
+    torch.manual_seed(0)
+    cfg = E.DMoEConfig(hidden=32, grid_size=(2, 2), k=2, num_layers=1, in_features=12, tokens_per_rank=32, lr=3e-3,
+                       trainer_microbatches=4)
+    tr = DMoETrainer(cfg)
+    x, y = torch.randn(32, 12), torch.randint(0, 10, (32,))
+    l0 = tr.train_step(x, y)
+    assert int(tr.model.blocks[0].shard.step.max()) == 4 and tr.step_count == 1     # experts: 4 updates, trainer: 1
+    losses = [tr.train_step(x, y) for _ in range(20)]
+    assert losses[-1] < 0.6 * l0

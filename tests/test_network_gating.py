@@ -167,3 +167,39 @@ def test_gating_function_end_to_end_and_fault_tolerance():
         gate(x2)
     gate.close()
     server.shutdown()
+
+
+def test_dht_rejects_malformed_and_executable_messages():
+    """the DHT envelope is msgpack with validated fields — nothing from the network is ever unpickled, and ids that
+    are not 20 bytes never reach the native routing table"""
+    import os
+    import pickle
+    import msgpack
+    from lah_b200.network import dht, _loads_value
+    good = dict(t="q", id=os.urandom(8), m="find_node", sender=os.urandom(20), target=os.urandom(20))
+    assert dht._valid_message(good)
+    for bad in (dict(good, sender=b"short"), dict(good, target=b"x" * 19), dict(good, m="exec"), dict(good, id=b"1"),
+                dict(good, t="z"), dict(good, nodes=[[os.urandom(20), ["not an ip", 5]]]),
+                dict(good, nodes=[[os.urandom(3), ["127.0.0.1", 5]]]), {k: v for k, v in good.items() if k != "target"}):
+        assert not dht._valid_message(bad), bad
+    node = dht.DHTNode()
+    proto = dht._Protocol(node)
+
+    class Boom:
+        def __reduce__(self):
+            return (os.system, ("echo pwned > /tmp/lah_dht_pwned",))
+
+    proto.datagram_received(pickle.dumps(Boom()), ("127.0.0.1", 1))          # a pickle is just an invalid msgpack message
+    proto.datagram_received(msgpack.packb(dict(good, target=b"abc"), use_bin_type=True), ("127.0.0.1", 1))
+    assert not os.path.exists("/tmp/lah_dht_pwned") and len(node.table) == 0
+    table = dht.RoutingTable(os.urandom(20))
+    assert not table.add(b"short-id", ("127.0.0.1", 1))
+    import pytest
+    with pytest.raises(ValueError):
+        table.closest(b"way-too-short")
+    # stored values: the reference's pickled records load, anything naming other globals does not
+    import datetime
+    rec = ((("127.0.0.1", 8080)), datetime.datetime.now())
+    assert _loads_value(pickle.dumps(rec))[0] == ("127.0.0.1", 8080)
+    with pytest.raises(pickle.UnpicklingError):
+        _loads_value(pickle.dumps(Boom()))
