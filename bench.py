@@ -152,6 +152,15 @@ def max_over_ranks(value, world):
     return float(t.item())
 
 
+def gather_ranks(value, world):
+    if world == 1:
+        return [round(value, 4)]
+    import torch.distributed as dist
+    out = [torch.zeros(1, dtype=torch.float64, device="cuda") for _ in range(world)]
+    dist.all_gather(out, torch.tensor([value], dtype=torch.float64, device="cuda"))
+    return [round(float(t.item()), 4) for t in out]
+
+
 def barrier_sync(world):
     torch.cuda.synchronize()
     if world > 1:
@@ -341,7 +350,9 @@ def _measure_ours(args, rank, world, local_rank, B, path="auto", tag="named", st
     if profiling:
         torch.cuda.profiler.stop()
     launches = native.launches()
-    exposed_ms = max_over_ranks(trainer.ctx.exposed_wait_ms(reset=True) / steps, world)
+    exposed_local = trainer.ctx.exposed_wait_ms(reset=True) / steps
+    exposed_ms = max_over_ranks(exposed_local, world)
+    exposed_ranks = gather_ranks(exposed_local, world)   # the rank with the SMALLEST wait is the step's straggler
     clocks = sampler.stop()
     check_all_ranks()
     global_batch = B * world
@@ -379,6 +390,7 @@ def _measure_ours(args, rank, world, local_rank, B, path="auto", tag="named", st
         routing.append({"active_experts": int((rows > 0).sum()), "max_rows": int(rows.max()), "mean_rows": float(rows.mean()),
                         "padded_rows": int(block.ws.total_rows.item()),
                         "shadowed_experts": int((block.ws.shadow_info.view(-1, 4)[:, 0] >= 0).sum())})
+    hottest = [int(max_over_ranks(float(r["max_rows"]), world)) for r in routing]   # over ALL ranks (load skew)
     # step roofline in the weight-streaming regime: every ACTIVE expert streams its bf16 weights twice (forward, dgrad) and
     # its fp32 optimizer state once (34 B / parameter with the fused wgrad+AMSGrad kernel); rank 0's share
     per_expert = sum(int(torch.tensor(s).prod()) for s in cfg.seg_shapes().values())
@@ -403,7 +415,8 @@ def _measure_ours(args, rank, world, local_rank, B, path="auto", tag="named", st
                    "gate": cfg.gate_mode + (" (LayerNorm(x) @ normalize(keys); gate params not trained, exactly like the reference's EmulatedDMoE)" if cfg.gate_mode == "emulator" else " (trainable product-key proj, lib.GatingFunction)"),
                    "l2_policy": "working set per step (optimizer state + weights of the active experts, >10 GB) exceeds the 126 MB L2; no explicit flush"},
         "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "routing_rank0": routing,
-        "exposed_comm_wait_ms_per_step": exposed_ms, "stage_ms_rank0": stage_ms,
+        "exposed_comm_wait_ms_per_step": exposed_ms, "exposed_comm_wait_ms_per_rank": exposed_ranks,
+        "hottest_expert_rows_per_layer": hottest, "stage_ms_rank0": stage_ms,
         "loss_first_last": [loss_curve[0], loss_curve[-1]] if loss_curve else None,
         "roofline": {"active_experts_rank0": active_total, "ideal_ms_hbm_bound_rank0": round(ideal_ms, 3),
                      "frac_of_measured_copy": round(ideal_ms / (ms / steps), 3) if trainer.ctx.small else None,

@@ -85,7 +85,10 @@ constexpr int B_BYTES = BN_MAX * BK * 2;      // 16 KB (only box_rows * 128 B ar
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
 constexpr int QD = 4;                         // depth of the tile queue (dynamic scheduler)
-constexpr int SMEM_TOTAL = BAR_OFFSET + (2 * STAGES + 4 + 2 * QD) * 8 + QD * 4 + 16 + 1024;
+constexpr int MAX_G = 1023;                   // groups per launch (prefix table of 128-token chunks lives in smem)
+constexpr int CUM_OFFSET = BAR_OFFSET + (2 * STAGES + 4 + 2 * QD) * 8 + QD * 4 + 16;
+constexpr int SMEM_TOTAL = CUM_OFFSET + (MAX_G + 1) * 4 + 1024;
+static_assert(SMEM_TOTAL <= 232448, "shared memory budget");
 
 struct Params {
     int G, M_out, K;          // groups, output features (rows of the weight operand), reduction length
@@ -106,8 +109,21 @@ struct Params {
 __device__ __forceinline__ int box_rows_of(int nn) { return nn <= 16 ? 16 : (nn <= 32 ? 32 : (nn <= 64 ? 64 : 128)); }
 
 // Tiles are handed out DYNAMICALLY: SMs do not get equal shares of HBM bandwidth (ncu on the static version: SMs idle 15-20 %
-// of the kernel waiting for the slowest one), so the TMA-producer thread of every CTA draws the next (group, 128-row slice)
-// from a global counter and publishes it to the other roles of its CTA through a small smem queue.
+// of the kernel waiting for the slowest one), so the TMA-producer thread of every CTA draws the next tile from a global
+// counter and publishes it to the other roles of its CTA through a small smem queue.
+// A tile is (group, 128-token chunk, 128-feature slice): a HOT expert (routing collapses while training; with 8 experts per
+// rank one of them can hold > 1000 of the rank's rows) is split over as many CTAs as it has chunks instead of one CTA
+// walking all of its chunks back to back - the slowest rank of a step is the one that owns the hottest expert, and every
+// other rank waits for it in the combine.  Every CTA builds the prefix table of chunks per group in shared memory.
+__device__ __forceinline__ int find_group(const int* cum, int G, int gc) {   // largest g with cum[g] <= gc
+    int lo = 0, hi = G - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (cum[mid] <= gc) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
 template <bool A_MN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 swapab_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB16,
@@ -123,10 +139,26 @@ swapab_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const __g
     uint64_t* q_empty = q_full + QD;
     volatile int* q_tile = reinterpret_cast<volatile int*>(q_empty + QD);
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(const_cast<int*>(q_tile) + QD);
+    int* cum = reinterpret_cast<int*>(smem + CUM_OFFSET);   // cum[g] = 128-token chunks of the groups before g
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
+    if (warp == 2) {   // prefix table of chunks (warp scan, 32 groups per round)
+        int carry = 0;
+        for (int base = 0; base < p.G; base += 32) {
+            const int g = base + lane;
+            int x = g < p.G ? (__ldg(p.group_rows + g) + BN_MAX - 1) / BN_MAX : 0;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, x, d);
+                if (lane >= d) x += y;
+            }
+            if (g < p.G) cum[g + 1] = carry + x;
+            carry += __shfl_sync(0xffffffffu, x, 31);
+        }
+        if (lane == 0) cum[0] = 0;
+    }
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB16);
@@ -154,7 +186,7 @@ swapab_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const __g
     const uint32_t tmem_base = *tmem_ptr;
 
     const int m_slices = p.M_out / BM;
-    const int total = p.G * m_slices;
+    const int total = cum[p.G] * m_slices;
     const int num_kb = p.K / BK;
 
     if (warp == 0 && lane == 0) {
@@ -170,14 +202,7 @@ swapab_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const __g
         int stage = 0, qi = 0;
         uint32_t phase = 0, qphase = 0;
         while (true) {
-            int tile;
-            while (true) {   // draw the next tile of an ACTIVE group; a drawn tile of an empty group skips the whole group
-                tile = atomicAdd(p.tile_counter, 1);
-                if (tile >= total) break;
-                const int g = tile / m_slices;
-                if (__ldg(p.group_rows + g) > 0) break;
-                atomicMax(p.tile_counter, (g + 1) * m_slices);
-            }
+            const int tile = atomicAdd(p.tile_counter, 1);
             mbar_wait(&q_empty[qi], qphase ^ 1);
             q_tile[qi] = tile;
             mbar_arrive(&q_full[qi]);
@@ -186,30 +211,30 @@ swapab_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const __g
                 qphase ^= 1;
             }
             if (tile >= total) break;
-            const int g = tile / m_slices, ms = tile - g * m_slices;
+            const int gc = tile / m_slices, ms = tile - gc * m_slices;
+            const int g = find_group(cum, p.G, gc);
+            const int n0 = (gc - cum[g]) * BN_MAX;
             const int rows = __ldg(p.group_rows + g);
             const int off = __ldg(p.group_off + g);
-            for (int n0 = 0; n0 < rows; n0 += BN_MAX) {
-                const int box = box_rows_of(min(rows - n0, BN_MAX));
-                const CUtensorMap* tmB = box == 16 ? &tmB16 : (box == 32 ? &tmB32 : (box == 64 ? &tmB64 : &tmB128));
-                for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
-                    uint8_t* sa = smem + stage * STAGE_BYTES;
-                    uint8_t* sb = sa + A_BYTES;
-                    const int k = kb * BK;
-                    mbar_arrive_expect_tx(&full_bar[stage], A_BYTES + box * 128);
-                    if (!A_MN) {
-                        tma_load_3d(sa, &tmA, &full_bar[stage], k, ms * BM, g);
-                    } else {
+            const int box = box_rows_of(min(rows - n0, BN_MAX));
+            const CUtensorMap* tmB = box == 16 ? &tmB16 : (box == 32 ? &tmB32 : (box == 64 ? &tmB64 : &tmB128));
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                uint8_t* sa = smem + stage * STAGE_BYTES;
+                uint8_t* sb = sa + A_BYTES;
+                const int k = kb * BK;
+                mbar_arrive_expect_tx(&full_bar[stage], A_BYTES + box * 128);
+                if (!A_MN) {
+                    tma_load_3d(sa, &tmA, &full_bar[stage], k, ms * BM, g);
+                } else {
 #pragma unroll
-                        for (int i = 0; i < BM / 64; ++i)
-                            tma_load_3d(sa + i * (BK * 128), &tmA, &full_bar[stage], ms * BM + i * 64, k, g);
-                    }
-                    tma_load_2d(sb, tmB, &full_bar[stage], k, off + n0);
-                    if (++stage == STAGES) {
-                        stage = 0;
-                        phase ^= 1;
-                    }
+                    for (int i = 0; i < BM / 64; ++i)
+                        tma_load_3d(sa + i * (BK * 128), &tmA, &full_bar[stage], ms * BM + i * 64, k, g);
+                }
+                tma_load_2d(sb, tmB, &full_bar[stage], k, off + n0);
+                if (++stage == STAGES) {
+                    stage = 0;
+                    phase ^= 1;
                 }
             }
         }
@@ -229,37 +254,35 @@ swapab_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const __g
                 qphase ^= 1;
             }
             if (tile >= total) break;
-            const int g = tile / m_slices;
-            const int rows = __ldg(p.group_rows + g);
-            for (int n0 = 0; n0 < rows; n0 += BN_MAX) {
-                const int nn = min(rows - n0, BN_MAX);
-                const uint32_t n16 = static_cast<uint32_t>((nn + 15) & ~15);
-                const uint32_t idesc = make_idesc_bf16_f32(BM, n16, A_MN ? 1u : 0u, 0u);
-                const int as = iter & 1;
-                const uint32_t aphase = (iter >> 1) & 1;
-                mbar_wait(&tmem_empty[as], aphase ^ 1);
+            const int gc = tile / m_slices;
+            const int g = find_group(cum, p.G, gc);
+            const int nn = min(__ldg(p.group_rows + g) - (gc - cum[g]) * BN_MAX, BN_MAX);
+            const uint32_t n16 = static_cast<uint32_t>((nn + 15) & ~15);
+            const uint32_t idesc = make_idesc_bf16_f32(BM, n16, A_MN ? 1u : 0u, 0u);
+            const int as = iter & 1;
+            const uint32_t aphase = (iter >> 1) & 1;
+            mbar_wait(&tmem_empty[as], aphase ^ 1);
+            tcgen05_fence_after();
+            const uint32_t tmem_d = tmem_base + as * BN_MAX;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(&full_bar[stage], phase);
                 tcgen05_fence_after();
-                const uint32_t tmem_d = tmem_base + as * BN_MAX;
-                for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(&full_bar[stage], phase);
-                    tcgen05_fence_after();
-                    const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-                    const uint32_t sb = sa + A_BYTES;
+                const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+                const uint32_t sb = sa + A_BYTES;
 #pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k) {
-                        const uint64_t da = make_smem_desc_sw128(sa + k * A_KSTEP, A_LBO, 1024);
-                        const uint64_t db = make_smem_desc_sw128(sb + k * (UMMA_K * 2), 0, 1024);
-                        umma_bf16_ss(tmem_d, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-                    }
-                    umma_commit(&empty_bar[stage]);
-                    if (kb == num_kb - 1) umma_commit(&tmem_full[as]);
-                    if (++stage == STAGES) {
-                        stage = 0;
-                        phase ^= 1;
-                    }
+                for (int k = 0; k < BK / UMMA_K; ++k) {
+                    const uint64_t da = make_smem_desc_sw128(sa + k * A_KSTEP, A_LBO, 1024);
+                    const uint64_t db = make_smem_desc_sw128(sb + k * (UMMA_K * 2), 0, 1024);
+                    umma_bf16_ss(tmem_d, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
                 }
-                ++iter;
+                umma_commit(&empty_bar[stage]);
+                if (kb == num_kb - 1) umma_commit(&tmem_full[as]);
+                if (++stage == STAGES) {
+                    stage = 0;
+                    phase ^= 1;
+                }
             }
+            ++iter;
         }
     } else if (warp >= 2) {
         // =============================================================== epilogue: thread = output feature, column = token
@@ -276,43 +299,42 @@ swapab_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const __g
                 qphase ^= 1;
             }
             if (tile >= total) break;
-            const int g = tile / m_slices, ms = tile - g * m_slices;
-            const int rows = __ldg(p.group_rows + g);
+            const int gc = tile / m_slices, ms = tile - gc * m_slices;
+            const int g = find_group(cum, p.G, gc);
+            const int n0 = (gc - cum[g]) * BN_MAX;
+            const int nn = min(__ldg(p.group_rows + g) - n0, BN_MAX);
             const int off = __ldg(p.group_off + g);
             const int feat = ms * BM + lane_group * 32 + lane;
             const float bias = p.bias ? __ldg(p.bias + static_cast<long long>(g) * p.M_out + feat) : 0.f;
-            for (int n0 = 0; n0 < rows; n0 += BN_MAX) {
-                const int nn = min(rows - n0, BN_MAX);
-                const int as = iter & 1;
-                const uint32_t aphase = (iter >> 1) & 1;
-                mbar_wait(&tmem_full[as], aphase);
-                tcgen05_fence_after();
-                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_group * 32) << 16) + as * BN_MAX;
-                // the padding rows of the group's last 16-row block are WRITTEN too (their inputs are zero rows, so they get
-                // bias / zero): every later kernel may then read whole 16-row blocks without meeting stale memory, and the
-                // k-step masked wgrad sees exact zeros there
-                const int n16 = (nn + 15) & ~15;
+            const int as = iter & 1;
+            const uint32_t aphase = (iter >> 1) & 1;
+            mbar_wait(&tmem_full[as], aphase);
+            tcgen05_fence_after();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_group * 32) << 16) + as * BN_MAX;
+            // the padding rows of the group's last 16-row block are WRITTEN too (their inputs are zero rows, so they get
+            // bias / zero): every later kernel may then read whole 16-row blocks without meeting stale memory, and the
+            // k-step masked wgrad sees exact zeros there
+            const int n16 = (nn + 15) & ~15;
 #pragma unroll 1
-                for (int c0 = 0; c0 < n16; c0 += 32) {
-                    uint32_t r[32];
-                    tmem_ld_32x32(taddr + c0, r);
-                    tmem_ld_wait();
-                    const int cn = min(32, n16 - c0);
-                    const long long row0 = off + n0 + c0;
+            for (int c0 = 0; c0 < n16; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld_32x32(taddr + c0, r);
+                tmem_ld_wait();
+                const int cn = min(32, n16 - c0);
+                const long long row0 = off + n0 + c0;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        if (j < cn) {
-                            float v = __uint_as_float(r[j]) + bias;
-                            if (p.residual) v += __bfloat162float(p.residual[(row0 + j) * p.ldr + feat]);
-                            p.out[(row0 + j) * p.ldo + feat] = __float2bfloat16(v);   // warp: 32 consecutive features = 64 B
-                        }
+                for (int j = 0; j < 32; ++j) {
+                    if (j < cn) {
+                        float v = __uint_as_float(r[j]) + bias;
+                        if (p.residual) v += __bfloat162float(p.residual[(row0 + j) * p.ldr + feat]);
+                        p.out[(row0 + j) * p.ldo + feat] = __float2bfloat16(v);   // warp: 32 consecutive features = 64 B
                     }
                 }
-                tcgen05_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&tmem_empty[as]);
-                ++iter;
             }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[as]);
+            ++iter;
         }
     }
     tcgen05_fence_before();
@@ -330,7 +352,10 @@ swapab_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const __g
 // =====================================================================================================================
 namespace wa {
 
-constexpr int OP_BYTES = 2 * (BK * BM * 2);              // A [64 t][128 n] + B [64 t][128 k] (two 64-wide MN atoms each)
+constexpr int WBK = 32;                                  // tokens per operand stage
+constexpr int OP_STAGES = 2;                             // a hot expert has tens of k-blocks: loads run ahead of the MMAs
+constexpr int OP_STAGE_BYTES = 2 * (WBK * BM * 2);       // A [32 t][128 n] + B [32 t][128 k] (two 64-wide MN atoms each)
+constexpr int OP_BYTES = OP_STAGES * OP_STAGE_BYTES;
 constexpr int SLOTS = 3;                                 // state ring per epilogue warp
 constexpr int STATE_TILE = 32 * 128;                     // 32 rows x 32 fp32 (one swizzle-128B atom group)
 constexpr int SLOT_BYTES = 4 * STATE_TILE;               // p, m, v, vmax
@@ -338,7 +363,7 @@ constexpr int STATE_OFFSET = OP_BYTES;
 constexpr int BAR_OFFSET = STATE_OFFSET + 4 * SLOTS * SLOT_BYTES;
 constexpr int QD = 4;                                    // depth of the tile queue (dynamic scheduler)
 constexpr int CHUNKS = BN_MAX / 32;                      // 32-column chunks per tile
-constexpr int SMEM_TOTAL = BAR_OFFSET + (2 + 4 + 4 * SLOTS + 2 * QD) * 8 + QD * 4 + 16 + 1024;
+constexpr int SMEM_TOTAL = BAR_OFFSET + (2 * OP_STAGES + 4 + 4 * SLOTS + 2 * QD) * 8 + QD * 4 + 16 + 1024;
 static_assert(SMEM_TOTAL <= 232448, "shared memory budget");
 
 struct Params {
@@ -365,8 +390,8 @@ wgrad_adam_kernel(const Params p, const __grid_constant__ CUtensorMap tmDY, cons
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* op_full = reinterpret_cast<uint64_t*>(smem + BAR_OFFSET);
-    uint64_t* op_empty = op_full + 1;
-    uint64_t* tmem_full = op_empty + 1;     // [2]
+    uint64_t* op_empty = op_full + OP_STAGES;
+    uint64_t* tmem_full = op_empty + OP_STAGES;   // [2]
     uint64_t* tmem_empty = tmem_full + 2;   // [2]
     uint64_t* st_full = tmem_empty + 2;     // [4 warps][SLOTS]
     uint64_t* q_full = st_full + 4 * SLOTS;
@@ -385,8 +410,10 @@ wgrad_adam_kernel(const Params p, const __grid_constant__ CUtensorMap tmDY, cons
         tma_prefetch_desc(&tmM);
         tma_prefetch_desc(&tmV);
         tma_prefetch_desc(&tmVM);
-        mbar_init(op_full, 1);
-        mbar_init(op_empty, 1);
+        for (int i = 0; i < OP_STAGES; ++i) {
+            mbar_init(&op_full[i], 1);
+            mbar_init(&op_empty[i], 1);
+        }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tmem_full[i], 1);
             mbar_init(&tmem_empty[i], 4);
@@ -424,7 +451,7 @@ wgrad_adam_kernel(const Params p, const __grid_constant__ CUtensorMap tmDY, cons
         // tiles are drawn from a global counter (work stealing: SMs see different HBM bandwidth, a static split leaves the
         // fast ones idle for ~15 % of the kernel) and published to the MMA thread and the epilogue warps through a queue
         uint32_t phase = 0, qphase = 0;
-        int qi = 0;
+        int qi = 0, stage = 0;
         while (true) {
             int tile;
             while (true) {
@@ -444,23 +471,28 @@ wgrad_adam_kernel(const Params p, const __grid_constant__ CUtensorMap tmDY, cons
             if (tile >= total) break;
             const Tile t = decode(tile);
             const int off = __ldg(p.group_off + t.g), rows = __ldg(p.group_rows + t.g);
-            for (int t0 = 0; t0 < rows; t0 += BK) {
-                mbar_wait(op_empty, phase ^ 1);
-                mbar_arrive_expect_tx(op_full, OP_BYTES);
-                uint8_t* sa = smem;
-                uint8_t* sb = smem + BK * BM * 2;
+            for (int t0 = 0; t0 < rows; t0 += WBK) {
+                mbar_wait(&op_empty[stage], phase ^ 1);
+                mbar_arrive_expect_tx(&op_full[stage], OP_STAGE_BYTES);
+                uint8_t* sa = smem + stage * OP_STAGE_BYTES;
+                uint8_t* sb = sa + WBK * BM * 2;
 #pragma unroll
-                for (int i = 0; i < BM / 64; ++i) tma_load_2d(sa + i * (BK * 128), &tmDY, op_full, t.mt * BM + i * 64, off + t0);
+                for (int i = 0; i < BM / 64; ++i)
+                    tma_load_2d(sa + i * (WBK * 128), &tmDY, &op_full[stage], t.mt * BM + i * 64, off + t0);
 #pragma unroll
-                for (int i = 0; i < BN_MAX / 64; ++i) tma_load_2d(sb + i * (BK * 128), &tmX, op_full, t.nt * BN_MAX + i * 64, off + t0);
-                phase ^= 1;
+                for (int i = 0; i < BN_MAX / 64; ++i)
+                    tma_load_2d(sb + i * (WBK * 128), &tmX, &op_full[stage], t.nt * BN_MAX + i * 64, off + t0);
+                if (++stage == OP_STAGES) {
+                    stage = 0;
+                    phase ^= 1;
+                }
             }
         }
     } else if (warp == 1 && lane == 0) {
         // =============================================================== MMA issuer: only ceil(rows/16) k-steps of a block
         constexpr uint32_t idesc = make_idesc_bf16_f32(BM, BN_MAX, 1u, 1u);
         uint32_t phase = 0, qphase = 0;
-        int iter = 0, qi = 0;
+        int iter = 0, qi = 0, stage = 0;
         while (true) {
             mbar_wait(&q_full[qi], qphase);
             const int tile = q_tile[qi];
@@ -477,20 +509,23 @@ wgrad_adam_kernel(const Params p, const __grid_constant__ CUtensorMap tmDY, cons
             mbar_wait(&tmem_empty[as], aphase ^ 1);
             tcgen05_fence_after();
             const uint32_t tmem_d = tmem_base + as * BN_MAX;
-            for (int t0 = 0; t0 < rows; t0 += BK) {
-                mbar_wait(op_full, phase);
+            for (int t0 = 0; t0 < rows; t0 += WBK) {
+                mbar_wait(&op_full[stage], phase);
                 tcgen05_fence_after();
-                const uint32_t sa = smem_u32(smem);
-                const uint32_t sb = sa + BK * BM * 2;
-                const int ksteps = min(BK / UMMA_K, (rows - t0 + UMMA_K - 1) / UMMA_K);
+                const uint32_t sa = smem_u32(smem + stage * OP_STAGE_BYTES);
+                const uint32_t sb = sa + WBK * BM * 2;
+                const int ksteps = min(WBK / UMMA_K, (rows - t0 + UMMA_K - 1) / UMMA_K);
                 for (int k = 0; k < ksteps; ++k) {
-                    const uint64_t da = make_smem_desc_sw128(sa + k * (UMMA_K * 128), BK * 128, 1024);
-                    const uint64_t db = make_smem_desc_sw128(sb + k * (UMMA_K * 128), BK * 128, 1024);
+                    const uint64_t da = make_smem_desc_sw128(sa + k * (UMMA_K * 128), WBK * 128, 1024);
+                    const uint64_t db = make_smem_desc_sw128(sb + k * (UMMA_K * 128), WBK * 128, 1024);
                     umma_bf16_ss(tmem_d, da, db, idesc, (t0 > 0 || k > 0) ? 1u : 0u);
                 }
-                umma_commit(op_empty);
-                if (t0 + BK >= rows) umma_commit(&tmem_full[as]);
-                phase ^= 1;
+                umma_commit(&op_empty[stage]);
+                if (t0 + WBK >= rows) umma_commit(&tmem_full[as]);
+                if (++stage == OP_STAGES) {
+                    stage = 0;
+                    phase ^= 1;
+                }
             }
             ++iter;
         }
@@ -662,7 +697,7 @@ int lah_swapab_linear(const void* x, long long ldx, int x_rows, const void* W, i
                       void* out, long long ldo, const int* group_off, const int* group_rows, const float* bias,
                       const void* residual, long long ldr, const int* wait_flags, int wait_count, int wait_epoch,
                       const int* epoch_base, int* status, int max_ctas, cudaStream_t st) {
-    if ((K % BK) || (M_out % BM) || (ldx % 8)) return -2;
+    if ((K % BK) || (M_out % BM) || (ldx % 8) || G > sab::MAX_G) return -2;
     CUtensorMap tmA, tmB[4];
     if (!a_mn) {
         uint64_t dims[3] = {(uint64_t)K, (uint64_t)M_out, (uint64_t)G};
@@ -691,12 +726,14 @@ int lah_swapab_linear(const void* x, long long ldx, int x_rows, const void* W, i
     p.wait_epoch = wait_epoch; p.epoch_base = epoch_base ? epoch_base : lah_get_epoch_base(); p.status = status;
     p.tile_counter = tile_counter();
     if (!p.tile_counter) return -3;
-    const int total = G * (M_out / BM);
-    if (total <= 0) return 0;
+    // upper bound of the tile count (the real one depends on the device-side row counts): every group has at least one
+    // 128-token chunk per 128-feature slice, and all groups together at most x_rows / 128 + G chunks
+    const long long total = 1ll * (M_out / BM) * (G + x_rows / BN_MAX);
+    if (total <= 0 || G <= 0) return 0;
     if (cudaMemsetAsync(p.tile_counter, 0, sizeof(int), st) != cudaSuccess) return -4;
     int ctas = num_sms();
     if (max_ctas > 0 && max_ctas < ctas) ctas = max_ctas;
-    if (total < ctas) ctas = total;
+    if (total < ctas) ctas = static_cast<int>(total);
     static bool configured[2] = {false, false};
     if (!a_mn) {
         if (!configured[0]) {
@@ -726,14 +763,14 @@ int lah_wgrad_adam(const void* dy, long long lddy, const void* x, long long ldx,
     {
         uint64_t dims[2] = {(uint64_t)N, (uint64_t)total_rows};
         uint64_t str[1] = {(uint64_t)lddy * 2};
-        uint32_t box[2] = {64, BK};
+        uint32_t box[2] = {64, wa::WBK};
         int r = make_tmap(&tmDY, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dy, 2, dims, str, box);
         if (r) return r;
     }
     {
         uint64_t dims[2] = {(uint64_t)K, (uint64_t)total_rows};
         uint64_t str[1] = {(uint64_t)ldx * 2};
-        uint32_t box[2] = {64, BK};
+        uint32_t box[2] = {64, wa::WBK};
         int r = make_tmap(&tmX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, x, 2, dims, str, box);
         if (r) return r;
     }

@@ -61,7 +61,7 @@ def timeit(fn, iters=20, flush=None):
 
 def check_swapab():
     torch.manual_seed(0)
-    rows_list = [0, 1, 16, 17, 63, 128, 130, 300, 5, 0, 64, 33]
+    rows_list = [0, 1, 16, 17, 63, 128, 130, 300, 5, 0, 64, 33, 1100, 257]
     G = len(rows_list)
     off, rows, total = make_groups(rows_list)
     for (K_in, M_out) in [(512, 2048), (2048, 2048), (2048, 512)]:
@@ -91,7 +91,7 @@ def check_swapab():
 
 def check_wgrad_adam():
     torch.manual_seed(1)
-    rows_list = [0, 1, 16, 17, 70, 200, 5]
+    rows_list = [0, 1, 16, 17, 70, 200, 5, 33, 600]
     G = len(rows_list)
     off, rows, total = make_groups(rows_list)
     for (N, Kd) in [(256, 128), (2048, 512), (512, 2048)]:
@@ -173,9 +173,43 @@ def perf():
            frac_of_measured_copy=p.numel() * 38 / ms2 / 1e6 / HBM)
 
 
+def perf_skew():
+    """one rank of the 8-GPU named config: 8 experts, 1024 routed rows, one HOT expert (collapsed routing).  The tile of a
+    hot expert must not serialise the launch: chunk-parallel swap-AB tiles, pipelined k-blocks in the fused wgrad"""
+    torch.manual_seed(3)
+    G, H, I = 8, 512, 2048
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    for tag, rows_list in [("uniform128", [128] * 8), ("hot1500", [1500, 200, 100, 60, 40, 30, 20, 16]),
+                           ("hot2048", [2048, 0, 0, 0, 0, 0, 0, 0])]:
+        off, rows, total = make_groups(rows_list)
+        a = torch.randn(total, I, device="cuda").to(torch.bfloat16)
+        x = torch.randn(total, H, device="cuda").to(torch.bfloat16)
+        w1 = torch.randn(G, I, H, device="cuda").to(torch.bfloat16)
+        w2 = torch.randn(G, I, I, device="cuda").to(torch.bfloat16)
+        h = torch.empty(total, I, device="cuda", dtype=torch.bfloat16)
+        y = torch.empty(total, H, device="cuda", dtype=torch.bfloat16)
+        out = {}
+        out["fwd1_ms"] = timeit(lambda: K.swapab_linear(x, w1, off, rows, out=h), flush=flush)
+        out["fwd2_ms"] = timeit(lambda: K.swapab_linear(a, w2, off, rows, out=h), flush=flush)
+        out["dgrad2_ms"] = timeit(lambda: K.swapab_linear(a, w2, off, rows, out=h, w_is_kn=True), flush=flush)
+        out["dgrad1_ms"] = timeit(lambda: K.swapab_linear(a, w1, off, rows, out=y, w_is_kn=True), flush=flush)
+        out["fwd2_52ctas_ms"] = timeit(lambda: K.swapab_linear(a, w2, off, rows, out=h, max_ctas=52), flush=flush)
+        p = torch.randn(G, I, I, device="cuda")
+        m, v, vmax = torch.zeros_like(p), torch.zeros_like(p), torch.zeros_like(p)
+        pb = torch.zeros(G, I, I, device="cuda", dtype=torch.bfloat16)
+        step = torch.ones(G, dtype=torch.int32, device="cuda")
+        dy = (torch.randn(total, I, device="cuda") * 0.1).to(torch.bfloat16)
+        out["wgrad_adam_w2_ms"] = timeit(lambda: K.wgrad_adam(dy, a, off, rows, p=p, m=m, v=v, vmax=vmax, p_bf16=pb, step=step),
+                                         flush=flush)
+        active = sum(1 for r in rows_list if r > 0)
+        out["wgrad_adam_TBps"] = active * I * I * 34 / out["wgrad_adam_w2_ms"] / 1e9
+        record("perf_skew_" + tag, ok=True, **out)
+
+
 def main():
     print("device:", torch.cuda.get_device_name(0), flush=True)
-    fns = [perf] if "--perf-only" in sys.argv else [check_swapab, check_wgrad_adam] + ([perf] if "--perf" in sys.argv else [])
+    fns = [perf, perf_skew] if "--perf-only" in sys.argv else \
+        [check_swapab, check_wgrad_adam] + ([perf, perf_skew] if "--perf" in sys.argv else [])
     for fn in fns:
         try:
             fn()
