@@ -247,6 +247,18 @@ def run_ours(args):
                                                            "steps", "warmup", "loss_first_last")}
         except Exception as e:
             extras["saturated"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+        if world > 1 and args.saturated_batch % world == 0:
+            # STRONG scaling of the saturated regime: the same GLOBAL batch (the 1-GPU "saturated" field) split over N ranks
+            try:
+                ss = _measure_ours(args, rank, world, local_rank, args.saturated_batch // world, path="big", tag="strong",
+                                   steps=max(3, min(args.steps, 10)), warmup=3)
+                if ss:
+                    extras["strong_scaling_saturated"] = {
+                        "global_batch": args.saturated_batch, "scaling": "strong",
+                        **{k: ss[k] for k in ("value", "unit", "ms_per_step", "exposed_comm_wait_ms_per_step", "steps", "warmup")},
+                        "e2e_ms_per_step": ss["e2e"]["ms_per_step"] if ss.get("e2e") else None}
+            except Exception as e:
+                extras["strong_scaling_saturated"] = {"error": f"{type(e).__name__}: {e}"[:300]}
     if not args.no_extra_configs:
         # BASELINE.json configs 5 (10 % expert failures, every N) and 4 (4096 experts = 1024 x 4, FP8 forward GEMMs, 64 trainers x
         # batch 8; needs the 8-GPU box: 25.8 B expert parameters + AMSGrad state = 71 GB per rank)
