@@ -79,8 +79,43 @@ class ClockSampler:
 
     def __init__(self, gpu_index):
         self.gpu, self.proc, self.path = gpu_index, None, None
+        self.thread, self.stop_flag, self.samples = None, threading.Event(), []
+
+    # NVML in-process (a sample costs ~50 us, one every 4 ms): the timed region of the named config is only tens of ms long at
+    # 8 GPUs, shorter than nvidia-smi's start-up, so a subprocess sampler would return nothing.  nvidia-smi is the fallback.
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            uuid = str(torch.cuda.get_device_properties(self.gpu).uuid)
+            return pynvml, pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+        except Exception:
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            index = int(visible.split(",")[self.gpu]) if visible and visible.split(",")[self.gpu].isdigit() else self.gpu
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(index)
+
+    def _nvml_loop(self, nv, handle):
+        names = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap,
+                 "hw_power_brake_slowdown": nv.nvmlClocksEventReasonHwPowerBrakeSlowdown}
+        mx = nv.nvmlDeviceGetMaxClockInfo(handle, nv.NVML_CLOCK_SM)
+        while not self.stop_flag.is_set():
+            try:
+                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(handle)
+                self.samples.append((float(nv.nvmlDeviceGetClockInfo(handle, nv.NVML_CLOCK_SM)), float(mx),
+                                     nv.nvmlDeviceGetPowerUsage(handle) / 1e3, [k for k, bit in names.items() if mask & bit]))
+            except Exception:
+                pass
+            self.stop_flag.wait(0.004)
 
     def start(self):
+        try:
+            nv, handle = self._nvml_handle()
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, handle), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
         try:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
@@ -92,6 +127,15 @@ class ClockSampler:
 
     def stop(self):
         out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[])
+        if self.thread is not None:
+            self.stop_flag.set()
+            self.thread.join(timeout=2)
+            if self.samples:
+                sm = sorted(s[0] for s in self.samples)
+                out = dict(sm_mhz=sm[len(sm) // 2], sm_min_mhz=sm[0], sm_max_mhz=max(s[1] for s in self.samples),
+                           power_w_max=max(s[2] for s in self.samples), samples=len(sm), sampler="nvml, every 4 ms",
+                           reasons=sorted({r for s in self.samples for r in s[3]}))
+            return out
         if self.proc is None:
             return out
         time.sleep(0.15)
@@ -119,7 +163,7 @@ class ClockSampler:
         if sm:
             loaded = sorted(sm)[len(sm) // 2]
             out = dict(sm_mhz=loaded, sm_max_mhz=max(mx), power_w_max=max(power) if power else None,
-                       samples=len(sm), reasons=sorted(reasons))
+                       samples=len(sm), sampler="nvidia-smi -lms 100", reasons=sorted(reasons))
         return out
 
 
