@@ -215,6 +215,7 @@ class DMoETrainer:
         timer = self.ctx.timer if self.cuda else None
         if self.cuda:
             self.ctx.begin_step()
+            self.ctx.defer_join = True   # this step joins the optimizer stream itself (below), not at the end of backward()
         if timer is not None:
             timer.start()
         m = max(1, int(self.cfg.trainer_microbatches))
@@ -227,8 +228,6 @@ class DMoETrainer:
             if not self.cuda:
                 for block in self.model.blocks:
                     block.apply_expert_gradients_ref()
-            if self.cuda:
-                self.ctx.join_optimizer_stream()   # the expert optimizers of this step (second stream) complete inside the step
         else:
             # several trainers per rank (reference: num_trainers threads, each with its own small batch): the batch is processed
             # as m micro-batches ONE AFTER THE OTHER; every micro-batch's backward steps the experts it used (so later trainers
@@ -257,6 +256,11 @@ class DMoETrainer:
                 self._stale_ring[-1].copy_(self.flat_g)
                 self.flat_g.copy_(oldest)
         self._trainer_optimizer_step()
+        if self.cuda:
+            # the expert optimizers of this step (second stream) complete inside the step; joined AFTER the trainer-side
+            # all-reduce + AMSGrad so that the last layer's expert updates overlap with them
+            self.ctx.join_optimizer_stream()
+            self.ctx.defer_join = False
         if timer is not None:
             timer.mark("trainer_adam")
             if timer.enabled:
