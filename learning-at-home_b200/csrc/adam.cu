@@ -151,7 +151,7 @@ int lah_adam_step(float* p, float* g, float* m, float* v, float* vmax, void* p_b
                   const int* step, const int* group_rows, int step_scalar, float lr, float beta1, float beta2, float eps,
                   float weight_decay, int amsgrad, int zero_mask, int world, long long peer_grad_off,
                   const unsigned long long* peer_bases, float grad_scale, int G_active, const int* shadow_of,
-                  long long shadow_g_off, int me, int seg_mask, int dead_mask, int max_blocks, cudaStream_t st) {
+                  long long shadow_g_off, int me, int seg_mask, int dead_mask, cudaStream_t st) {
     if (num_segs < 1 || num_segs > 12) return -2;
     AdamArgs a;
     a.num_segs = num_segs;
@@ -194,9 +194,6 @@ int lah_adam_step(float* p, float* g, float* m, float* v, float* vmax, void* p_b
     if (span <= 0) return 0;
     long long blocks = (span / 4 + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
-    // overlap mode (the kernel runs on a second stream next to compute-bound GEMM CTAs): a bounded grid keeps thread slots
-    // free on every SM, so the 1-CTA-per-SM GEMM kernels of the main stream are never locked out by resident Adam blocks
-    if (max_blocks > 0 && blocks > max_blocks) blocks = max_blocks;
     adam_kernel<<<(int)blocks, 256, 0, st>>>(a);
     return -(int)cudaGetLastError();
 }

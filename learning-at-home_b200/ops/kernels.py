@@ -53,7 +53,7 @@ def _lib():
         "lah_signal_wait": [L, I, I, I, I, P, P],
         "lah_combine_rows": [L, P, P, P, P, I, I, I, I, L, I, I, I, I, P, P, P],
         "lah_gate_bwd": [L, P, P, P, P, P, I, I, I, I, P, I, P, P],
-        "lah_adam_step": [P, P, P, P, P, P, I, P, I, P, P, I, Fl, Fl, Fl, Fl, Fl, I, I, I, L, P, Fl, I, P, L, I, I, I, I, P],
+        "lah_adam_step": [P, P, P, P, P, P, I, P, I, P, P, I, Fl, Fl, Fl, Fl, Fl, I, I, I, L, P, Fl, I, P, L, I, I, I, P],
         "lah_bump_steps": [P, P, I, P],
         "lah_cast_bf16": [P, P, L, P],
         "lah_attention_fwd": [P, P, P, I, I, I, P],
@@ -312,7 +312,7 @@ def attention_ref(qkv, num_heads, seq_len=512):
 def adam_step(p, g, m, v, vmax, p_bf16, seg_sizes, G, *, step=None, group_rows=None, step_scalar=0, lr=1e-3,
               betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, amsgrad=True, zero_mask=0, world=1,
               peer_grad_off=-1, peer_bases=None, grad_scale=1.0, G_active=0, shadow_of=None, shadow_g_off=-1, me=0,
-              seg_mask=0, dead_mask=0, max_blocks=0):
+              seg_mask=0, dead_mask=0):
     arr = None
     if peer_bases is not None:
         arr = (c_ull * len(peer_bases))(*[int(b) for b in peer_bases])
@@ -333,7 +333,7 @@ def adam_step(p, g, m, v, vmax, p_bf16, seg_sizes, G, *, step=None, group_rows=N
                                       int(amsgrad), int(zero_mask), world, peer_grad_off,
                                       ctypes.cast(arr, c_void_p) if arr is not None else c_void_p(0), grad_scale,
                                       int(G_active), ptr(shadow_of), int(shadow_g_off), int(me), int(seg_mask),
-                                      int(dead_mask), int(max_blocks), stream_ptr()), "lah_adam_step")
+                                      int(dead_mask), stream_ptr()), "lah_adam_step")
     native.count_launch()
 
 

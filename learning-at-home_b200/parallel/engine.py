@@ -84,12 +84,6 @@ class DMoEConfig:
     # 116 of 148 on one GPU, 96 when the experts are sharded (measured: 1 GPU 10.96 -> 10.06 ms, 2 GPUs 7.08 -> 6.54 ms,
     # 4 GPUs 5.16 -> 4.32 ms per step; 64 and >= 132 are slower than no overlap — profiles/overlap_sweep_r2.md)
     optimizer_ctas: int = -1
-    # big path: the per-expert AMSGrad of layer L (bandwidth-bound, peer reads of the shadow gradients) runs on the second
-    # stream with a bounded grid (`adam_blocks_per_sm` 256-thread blocks per SM, co-resident with the compute-bound CTA-pair
-    # GEMMs) while the main stream already sends dX back and runs the backward of layer L-1: the optimizer leaves the critical
-    # path of the step AND of the peers waiting for this rank's dX.  (env LAH_BIG_ADAM_OVERLAP=0/1 overrides)
-    overlap_big_optimizer: bool = True
-    adam_blocks_per_sm: int = 2
     # asynchronous expert updates (reference: EmulatedDMoE.update_every_inputs / update_every_steps,
     # experiments/convergence/dmoe_emulator.py:70-77): an expert accumulates weight gradients and steps once it has seen
     # >= update_every_inputs rows or >= update_every_steps steps since its first pending row.  (0, 0) = step after every
@@ -212,9 +206,7 @@ class EngineContext:
         sms = torch.cuda.get_device_properties(self.device).multi_processor_count
         self.opt_ctas = octas if (self.small and 0 < octas < sms - 8) else 0     # CTAs of the optimizer stream (0: no overlap)
         self.chain_ctas = sms - self.opt_ctas if self.opt_ctas else 0            # CTA limit of the persistent chain kernels
-        big_overlap = (not self.small) and bool(int(_os.environ.get("LAH_BIG_ADAM_OVERLAP", int(cfg.overlap_big_optimizer))))
-        self.adam_blocks = sms * max(1, int(cfg.adam_blocks_per_sm)) if big_overlap else 0   # 0: optimizer on the main stream
-        self.opt_stream = torch.cuda.Stream(self.device) if (self.opt_ctas or big_overlap) else None
+        self.opt_stream = torch.cuda.Stream(self.device) if self.opt_ctas else None
         self._opt_pending = False
         self.defer_join = False   # DMoETrainer joins the optimizer stream itself, at the very end of its step
         K.set_poison_word(self.status)   # a step in which a peer timed out applies no optimizer update (the batch fails)
@@ -752,21 +744,12 @@ class FusedDMoE(nn.Module):
                             two_cta=c.two_cta)
         c.timer.mark("expert_ffn_bwd(wgrad+dgrad+ln)")
         # ---- expert-side optimizer step (reference: ExpertBackend.apply_gradients right after backward)
-        side = c.opt_stream if c.adam_blocks else None
+        # (measured: moving this AMSGrad to a second stream with a bounded grid buys nothing in the saturated regime — the GPU
+        # sits at its power cap there, 705 W / 1665 MHz, and the next layer's bandwidth-bound stages slow down by what the
+        # optimizer gains: 62.1 vs 62.2 ms on 1 GPU, 61.3 vs 62.3 ms on 2; gpurun calls 19 / 20)
         if c.S:  # the owners read every rank's partial gradients of the shadowed experts: all ranks must be done
-            K.signal_wait(c.flags_off, K.SLOT_SHADOW, epoch, c.status, signal=True, wait=side is None)
-        if side is None:
-            self.apply_expert_gradients()
-        else:
-            # second stream, ordered after this layer's wgrads; the main stream goes straight on to the dX combine.  The next
-            # write to this layer's gradient buffer / read of its weights is a whole step away, behind join_optimizer_stream()
-            main = torch.cuda.current_stream(c.device)
-            side.wait_stream(main)
-            with torch.cuda.stream(side):
-                if c.S:
-                    K.signal_wait(c.flags_off, K.SLOT_SHADOW, epoch, c.status, signal=False, wait=True)
-                self.apply_expert_gradients(max_blocks=c.adam_blocks)
-            c._opt_pending = True
+            K.signal_wait(c.flags_off, K.SLOT_SHADOW, epoch, c.status, signal=True, wait=True)
+        self.apply_expert_gradients()
         c.timer.mark("expert_adam")
         dx = torch.empty(B, cfg.hidden, dtype=torch.bfloat16, device=gy.device)
         K.combine_rows(c.dxd_off, idx, pair_row, None, dx, k, c.E_loc, flags_off=c.flags_off, slot=K.SLOT_DINPUT,
@@ -817,7 +800,7 @@ class FusedDMoE(nn.Module):
                     group_rows=ws.step_rows, zero_mask=SMALL_SEG_MASK, G_active=self.E_loc, seg_mask=SMALL_SEG_MASK, **opt)
         sh.w8_dirty = True
 
-    def apply_expert_gradients(self, max_blocks: int = 0):
+    def apply_expert_gradients(self):
         sh, cfg, ws, c = self.shard, self.cfg, self.ws, self.ctx
         rows, zero_mask = ws.step_rows, SMALL_SEG_MASK
         if cfg.accumulate:
@@ -836,7 +819,7 @@ class FusedDMoE(nn.Module):
                     group_rows=rows, lr=cfg.lr, betas=cfg.betas, eps=cfg.eps, amsgrad=cfg.amsgrad,
                     zero_mask=zero_mask, G_active=self.E_loc, world=c.world,
                     peer_bases=c.heap.peer_bases if c.S else None, shadow_of=ws.owned_shadow if c.S else None,
-                    shadow_g_off=sh.g_off, me=c.rank, max_blocks=max_blocks)
+                    shadow_g_off=sh.g_off, me=c.rank)
         sh.w8_dirty = True
 
     def failure_rate_ref(self) -> float:

@@ -103,34 +103,6 @@ def test_cuda_graph_step_equals_eager_step(path):
     assert losses[True][-1] == losses[True][-1]
 
 
-def test_big_path_optimizer_overlap_equals_serial(monkeypatch):
-    """big path: per-expert AMSGrad on the second stream (bounded grid, off the critical path) == the same step with the
-    optimizer on the launching stream"""
-    import lah_b200  # noqa
-    from lah_b200.parallel import engine as E
-    from lah_b200.parallel.trainer import DMoETrainer
-    cfg = E.DMoEConfig(hidden=512, grid_size=(16,), k=4, num_layers=3, tokens_per_rank=1024, gate_mode="emulator", lr=1e-4,
-                       expert_path="big")
-    torch.manual_seed(0)
-    xs = [torch.randn(1024, cfg.in_features, device="cuda") for _ in range(5)]
-    ys = [torch.randint(0, 10, (1024,), device="cuda") for _ in range(5)]
-    out = {}
-    for overlap in ("0", "1"):
-        monkeypatch.setenv("LAH_BIG_ADAM_OVERLAP", overlap)
-        t = DMoETrainer(cfg, use_graph=False)
-        assert (t.ctx.opt_stream is not None) == (overlap == "1") and not t.ctx.small
-        losses = [float(t.train_step_device(x, y)) for x, y in zip(xs, ys)]
-        torch.cuda.synchronize()
-        out[overlap] = (losses, [b.shard.p.clone() for b in t.model.blocks], [b.shard.step.clone() for b in t.model.blocks])
-        t.ctx.check_status()
-        t.close()
-    for a, b in zip(out["0"][0], out["1"][0]):
-        assert abs(a - b) < 5e-3 * max(1.0, abs(a)), (out["0"][0], out["1"][0])
-    for p0, p1, s0, s1 in zip(out["0"][1], out["1"][1], out["0"][2], out["1"][2]):
-        assert torch.equal(s0, s1) and int(s0.max()) == 5
-        assert float((p0 - p1).abs().mean()) < 2e-5, float((p0 - p1).abs().mean())
-
-
 def test_update_every_inputs_accumulates_like_the_emulator():
     """DMoEConfig.update_every_inputs / update_every_steps (dmoe_emulator.py:70-77): experts step only when due"""
     import lah_b200  # noqa
