@@ -12,7 +12,7 @@ torch.manual_seed(0)
 G, R = 64, 2048
 rows = G * R
 tg = torch.arange(G, device="cuda", dtype=torch.int32).repeat_interleave(R // 128)
-which = set(sys.argv[1:]) or {"fp8", "bf16", "attn", "ln"}
+which = set(sys.argv[1:]) or {"fp8", "bf16", "attn", "ln"}   # + "small"
 if "fp8" in which or "bf16" in which:
     N = Kd = 2048
     a = torch.randn(rows, Kd, device="cuda").to(torch.bfloat16)
@@ -41,5 +41,26 @@ if "ln" in which:
     for _ in range(2):
         K.ln_relu_fwd(h, gamma, beta, tg, out=a2, mean=mean, rstd=rstd)
     K.ln_relu_fwd(h, gamma, beta, tg, out=a2, mean=mean, rstd=rstd, quant=aq2)
+if "small" in which:
+    # the small-M kernels at (a) the named config: 64 experts x 16 rows, (b) one rank's share at 8 GPUs with a hot expert
+    H, I = 512, 2048
+    for rows_list in ([16] * 64, [1500, 200, 100, 60, 40, 30, 20, 16]):
+        Gs = len(rows_list)
+        padded = [(r + 15) // 16 * 16 for r in rows_list]
+        off = torch.tensor([sum(padded[:i]) for i in range(Gs)], dtype=torch.int32, device="cuda")
+        rws = torch.tensor(rows_list, dtype=torch.int32, device="cuda")
+        total = sum(padded)
+        act = torch.randn(total, I, device="cuda").to(torch.bfloat16)
+        w2 = torch.randn(Gs, I, I, device="cuda").to(torch.bfloat16)
+        hbuf = torch.empty(total, I, device="cuda", dtype=torch.bfloat16)
+        K.swapab_linear(act, w2, off, rws, out=hbuf)
+        K.swapab_linear(act, w2, off, rws, out=hbuf, w_is_kn=True)
+        p = torch.randn(Gs, I, I, device="cuda")
+        m, v, vmax = torch.zeros_like(p), torch.zeros_like(p), torch.zeros_like(p)
+        pb = torch.zeros(Gs, I, I, device="cuda", dtype=torch.bfloat16)
+        step = torch.ones(Gs, dtype=torch.int32, device="cuda")
+        dy = (torch.randn(total, I, device="cuda") * 0.1).to(torch.bfloat16)
+        K.wgrad_adam(dy, act, off, rws, p=p, m=m, v=v, vmax=vmax, p_bf16=pb, step=step)
+        del p, m, v, vmax, pb, w2
 torch.cuda.synchronize()
 print("prof_driver done")
