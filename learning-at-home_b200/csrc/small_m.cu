@@ -7,11 +7,12 @@
 //
 //   swapab_kernel      D^T[out_features, tokens] = W[out_features, K] * X^T[K, tokens]   ("swap-AB": the weights sit on
 //                      the 128-wide MMA-M side, the expert's 16..128 tokens on the MMA-N side, so a group of 16 rows
-//                      costs one N=16 instruction instead of a 256-row padded tile).  Each CTA streams a 128-row slice
-//                      of one expert's weight matrix through a 6-stage TMA ring exactly once.  A_MN selects dgrad
+//                      costs one N=16 instruction instead of a 256-row padded tile).  A tile = (expert, 128-token
+//                      chunk, 128-row slice of the weight matrix) streamed through a 6-stage TMA ring; experts with
+//                      more than 128 rows are spread over several CTAs (hot experts).  A_MN selects dgrad
 //                      (W^T read straight from the same [out, in] tensor as an MN-major operand).
-//   wgrad_adam_kernel  dW tile = dY^T X on tcgen05 (both operands MN-major, reduction over the expert's tokens = the
-//                      gradient reduction over all trainers that routed to it) with the per-expert AMSGrad step FUSED
+//   wgrad_adam_kernel  dW tile = dY^T X on tcgen05 (both operands MN-major, two 32-token stages, reduction over the
+//                      expert's tokens = the gradient reduction over all trainers that routed to it) with the per-expert AMSGrad step FUSED
 //                      INTO THE EPILOGUE: p / m / v / vmax tiles arrive through TMA (128B-swizzled smem, per-warp
 //                      3-slot ring), are updated in place from the TMEM accumulator and leave through TMA stores; the
 //                      bf16 mirror is written from registers.  The weight gradient never exists in HBM: 34 B / parameter
