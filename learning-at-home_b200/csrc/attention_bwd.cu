@@ -234,6 +234,38 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+// prologue: delta[t, h] = sum_d dO[t, h, d] * O[t, h, d]  (one warp per (token, head): 64 bf16 = one 128 B row segment each)
+__global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ out,
+                                                         float* __restrict__ delta, long long pairs) {
+    const long long w = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= pairs) return;
+    const __nv_bfloat162 a = reinterpret_cast<const __nv_bfloat162*>(dout + w * HEAD_DIM)[lane];
+    const __nv_bfloat162 b = reinterpret_cast<const __nv_bfloat162*>(out + w * HEAD_DIM)[lane];
+    float acc = __bfloat162float(a.x) * __bfloat162float(b.x) + __bfloat162float(a.y) * __bfloat162float(b.y);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+    if (lane == 0) delta[w] = acc;
+}
+
+// epilogue: dQ = sum of the per-key-block partials, written as bf16 into the Q third of dqkv
+__global__ void __launch_bounds__(256) attn_dq_reduce_kernel(const float* __restrict__ dq_part, bf16* __restrict__ dqkv,
+                                                             long long tokens, int d_model, int parts) {
+    const long long i4 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;   // float4 index inside [T, D]
+    const long long n4 = tokens * d_model / 4;
+    if (i4 >= n4) return;
+    float4 acc = reinterpret_cast<const float4*>(dq_part)[i4];
+    for (int p = 1; p < parts; ++p) {
+        const float4 t = reinterpret_cast<const float4*>(dq_part)[i4 + p * n4];
+        acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+    }
+    const long long e = i4 * 4, tok = e / d_model, col = e - tok * d_model;
+    uint2 q;
+    q.x = pack_bf16x2(acc.x, acc.y);
+    q.y = pack_bf16x2(acc.z, acc.w);
+    *reinterpret_cast<uint2*>(dqkv + tok * 3 * d_model + col) = q;
+}
+
 }  // namespace attnb
 }  // namespace lah
 
@@ -242,10 +274,11 @@ using namespace lah::attnb;
 
 extern "C" {
 
-// qkv [T, 3D] bf16 (forward input), dout [T, D] bf16, lse2 [T, H] fp32 (forward output), delta [T, H] fp32 = rowsum(dout o out)
-// -> dqkv [T, 3D] bf16: the K and V thirds are written here; dq_part [4, T, D] fp32 receives the four per-key-block partials of dQ
-int lah_attention_bwd(const void* qkv, const void* dout, const float* lse2, const float* delta, void* dqkv, float* dq_part,
-                      int batch, int num_heads, int d_model, cudaStream_t st) {
+// qkv [T, 3D] bf16 (forward input), out [T, D] bf16 (forward output), dout [T, D] bf16, lse2 [T, H] fp32 (forward output)
+// -> dqkv [T, 3D] bf16.  Scratch: delta [T, H] fp32 (rowsum(dout o out), computed here), dq_part [4, T, D] fp32 (the four
+// per-key-block partials of dQ, reduced into the Q third of dqkv here).  Three launches, no PyTorch ops around them.
+int lah_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse2, float* delta, void* dqkv,
+                      float* dq_part, int batch, int num_heads, int d_model, cudaStream_t st) {
     if (d_model != num_heads * HEAD_DIM) return -2;
     static PFN_encodeTiled fn = nullptr;
     if (!fn) {
@@ -282,9 +315,13 @@ int lah_attention_bwd(const void* qkv, const void* dout, const float* lse2, cons
     }
     if (batch <= 0) return 0;
     const float scale = 1.f / sqrtf((float)HEAD_DIM);
+    const long long tokens = (long long)batch * S_LEN, pairs = tokens * num_heads;
+    attn_delta_kernel<<<(unsigned)((pairs * 32 + 255) / 256), 256, 0, st>>>((const bf16*)dout, (const bf16*)out, delta, pairs);
     attention_bwd_kernel<<<batch * num_heads * (S_LEN / BLK), NUM_THREADS, SMEM_TOTAL, st>>>(
-        tm_qkv, tm_do, lse2, delta, (bf16*)dqkv, dq_part, (long long)batch * S_LEN, d_model, num_heads, scale,
+        tm_qkv, tm_do, lse2, delta, (bf16*)dqkv, dq_part, tokens, d_model, num_heads, scale,
         scale * 1.4426950408889634f);
+    attn_dq_reduce_kernel<<<(unsigned)((tokens * d_model / 4 + 255) / 256), 256, 0, st>>>(dq_part, (bf16*)dqkv, tokens, d_model,
+                                                                                         S_LEN / BLK);
     return -(int)cudaGetLastError();
 }
 

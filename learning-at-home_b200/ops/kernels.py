@@ -57,7 +57,7 @@ def _lib():
         "lah_bump_steps": [P, P, I, P],
         "lah_cast_bf16": [P, P, L, P],
         "lah_attention_fwd": [P, P, P, I, I, I, P],
-        "lah_attention_bwd": [P, P, P, P, P, P, I, I, I, P],
+        "lah_attention_bwd": [P, P, P, P, P, P, P, I, I, I, P],
         "lah_symm_alloc": [c_ull, ctypes.POINTER(c_void_p)],
         "lah_symm_free": [P],
         "lah_symm_get_handle": [P, ctypes.c_char_p],
@@ -286,13 +286,13 @@ def attention_bwd(qkv, out, dout, lse, num_heads):
     tokens, three_d = qkv.shape
     d_model = three_d // 3
     assert dout.dtype == torch.bfloat16 and dout.is_contiguous() and out.is_contiguous() and lse.dtype == torch.float32
-    delta = (dout.float() * out.float()).view(tokens, num_heads, d_model // num_heads).sum(-1).contiguous()
+    assert out.dtype == torch.bfloat16 and qkv.is_contiguous()
+    delta = torch.empty(tokens, num_heads, dtype=torch.float32, device=qkv.device)      # rowsum(dout o out), filled by the prologue kernel
     dqkv = torch.empty_like(qkv)
     dq_part = torch.empty(4, tokens, d_model, dtype=torch.float32, device=qkv.device)   # one partial per 128-key block
-    native.check(_lib().lah_attention_bwd(ptr(qkv), ptr(dout), ptr(lse), ptr(delta), ptr(dqkv), ptr(dq_part), tokens // 512,
-                                          num_heads, d_model, stream_ptr()), "lah_attention_bwd")
-    native.count_launch()
-    dqkv[:, :d_model].copy_(dq_part.sum(0))
+    native.check(_lib().lah_attention_bwd(ptr(qkv), ptr(out), ptr(dout), ptr(lse), ptr(delta), ptr(dqkv), ptr(dq_part),
+                                          tokens // 512, num_heads, d_model, stream_ptr()), "lah_attention_bwd")
+    native.count_launch(3)   # delta prologue, tcgen05 backward, dQ partial reduction
     return dqkv
 
 
