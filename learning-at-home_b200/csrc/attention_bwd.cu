@@ -43,7 +43,7 @@ constexpr int COL_S = 0, COL_DP = 128, COL_DV = 256, COL_DK = 320, COL_DQ = 384;
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
                      const float* __restrict__ lse2, const float* __restrict__ delta, bf16* __restrict__ dqkv,
-                     float* __restrict__ dq_part, long long total_tokens, int d_model, int num_heads, float scale,
+                     bf16* __restrict__ dq_part, long long total_tokens, int d_model, int num_heads, float scale,
                      float scale_log2e) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -181,18 +181,20 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
             mbar_arrive(p_full);
             mbar_wait(dq_full, i & 1);
             tcgen05_fence_after();
-            // partial dQ of THIS key block: plain 16 B stores of the thread's 256 contiguous bytes into slice j of dq_part
-            // ([4, T, D] fp32; the caller sums the four slices while casting to bf16) — no atomics
-            float4* dq = reinterpret_cast<float4*>(dq_part + (static_cast<long long>(j) * total_tokens + token) * d_model + head * HEAD_DIM);
+            // partial dQ of THIS key block: plain 16 B stores of the thread's 128 contiguous bytes into slice j of dq_part
+            // ([4, T, D] bf16; attn_dq_reduce_kernel sums the four slices in fp32) — no atomics, half the bytes of fp32 partials
+            int4* dq = reinterpret_cast<int4*>(dq_part + (static_cast<long long>(j) * total_tokens + token) * d_model + head * HEAD_DIM);
 #pragma unroll 1
             for (int c = 0; c < HEAD_DIM / 32; ++c) {
                 uint32_t r[32];
                 tmem_ld_32x32(lane_base + COL_DQ + c * 32, r);
                 tmem_ld_wait();
 #pragma unroll
-                for (int e = 0; e < 8; ++e)
-                    dq[c * 8 + e] = make_float4(__uint_as_float(r[4 * e]), __uint_as_float(r[4 * e + 1]), __uint_as_float(r[4 * e + 2]),
-                                                __uint_as_float(r[4 * e + 3]));
+                for (int e = 0; e < 4; ++e)
+                    dq[c * 4 + e] = make_int4(pack_bf16x2(__uint_as_float(r[8 * e]), __uint_as_float(r[8 * e + 1])),
+                                              pack_bf16x2(__uint_as_float(r[8 * e + 2]), __uint_as_float(r[8 * e + 3])),
+                                              pack_bf16x2(__uint_as_float(r[8 * e + 4]), __uint_as_float(r[8 * e + 5])),
+                                              pack_bf16x2(__uint_as_float(r[8 * e + 6]), __uint_as_float(r[8 * e + 7])));
             }
             tcgen05_fence_before();
         }
@@ -249,21 +251,27 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict_
 }
 
 // epilogue: dQ = sum of the per-key-block partials, written as bf16 into the Q third of dqkv
-__global__ void __launch_bounds__(256) attn_dq_reduce_kernel(const float* __restrict__ dq_part, bf16* __restrict__ dqkv,
+__global__ void __launch_bounds__(256) attn_dq_reduce_kernel(const bf16* __restrict__ dq_part, bf16* __restrict__ dqkv,
                                                              long long tokens, int d_model, int parts) {
-    const long long i4 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;   // float4 index inside [T, D]
-    const long long n4 = tokens * d_model / 4;
-    if (i4 >= n4) return;
-    float4 acc = reinterpret_cast<const float4*>(dq_part)[i4];
-    for (int p = 1; p < parts; ++p) {
-        const float4 t = reinterpret_cast<const float4*>(dq_part)[i4 + p * n4];
-        acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+    const long long i8 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;   // 8-element (16 B) index inside [T, D]
+    const long long n8 = tokens * d_model / 8;
+    if (i8 >= n8) return;
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    for (int p = 0; p < parts; ++p) {
+        const int4 t = reinterpret_cast<const int4*>(dq_part)[i8 + p * n8];
+        const uint32_t w[4] = {(uint32_t)t.x, (uint32_t)t.y, (uint32_t)t.z, (uint32_t)t.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float2 f = unpack_bf16x2(w[e]);
+            acc[2 * e] += f.x;
+            acc[2 * e + 1] += f.y;
+        }
     }
-    const long long e = i4 * 4, tok = e / d_model, col = e - tok * d_model;
-    uint2 q;
-    q.x = pack_bf16x2(acc.x, acc.y);
-    q.y = pack_bf16x2(acc.z, acc.w);
-    *reinterpret_cast<uint2*>(dqkv + tok * 3 * d_model + col) = q;
+    const long long el = i8 * 8, tok = el / d_model, col = el - tok * d_model;
+    *reinterpret_cast<int4*>(dqkv + tok * 3 * d_model + col) =
+        make_int4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]), pack_bf16x2(acc[6], acc[7]));
 }
 
 }  // namespace attnb
@@ -275,10 +283,10 @@ using namespace lah::attnb;
 extern "C" {
 
 // qkv [T, 3D] bf16 (forward input), out [T, D] bf16 (forward output), dout [T, D] bf16, lse2 [T, H] fp32 (forward output)
-// -> dqkv [T, 3D] bf16.  Scratch: delta [T, H] fp32 (rowsum(dout o out), computed here), dq_part [4, T, D] fp32 (the four
+// -> dqkv [T, 3D] bf16.  Scratch: delta [T, H] fp32 (rowsum(dout o out), computed here), dq_part [4, T, D] bf16 (the four
 // per-key-block partials of dQ, reduced into the Q third of dqkv here).  Three launches, no PyTorch ops around them.
 int lah_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse2, float* delta, void* dqkv,
-                      float* dq_part, int batch, int num_heads, int d_model, cudaStream_t st) {
+                      void* dq_part, int batch, int num_heads, int d_model, cudaStream_t st) {
     if (d_model != num_heads * HEAD_DIM) return -2;
     static PFN_encodeTiled fn = nullptr;
     if (!fn) {
@@ -318,9 +326,9 @@ int lah_attention_bwd(const void* qkv, const void* out, const void* dout, const 
     const long long tokens = (long long)batch * S_LEN, pairs = tokens * num_heads;
     attn_delta_kernel<<<(unsigned)((pairs * 32 + 255) / 256), 256, 0, st>>>((const bf16*)dout, (const bf16*)out, delta, pairs);
     attention_bwd_kernel<<<batch * num_heads * (S_LEN / BLK), NUM_THREADS, SMEM_TOTAL, st>>>(
-        tm_qkv, tm_do, lse2, delta, (bf16*)dqkv, dq_part, tokens, d_model, num_heads, scale,
+        tm_qkv, tm_do, lse2, delta, (bf16*)dqkv, (bf16*)dq_part, tokens, d_model, num_heads, scale,
         scale * 1.4426950408889634f);
-    attn_dq_reduce_kernel<<<(unsigned)((tokens * d_model / 4 + 255) / 256), 256, 0, st>>>(dq_part, (bf16*)dqkv, tokens, d_model,
+    attn_dq_reduce_kernel<<<(unsigned)((tokens * d_model / 8 + 255) / 256), 256, 0, st>>>((const bf16*)dq_part, (bf16*)dqkv, tokens, d_model,
                                                                                          S_LEN / BLK);
     return -(int)cudaGetLastError();
 }

@@ -289,7 +289,7 @@ def attention_bwd(qkv, out, dout, lse, num_heads):
     assert out.dtype == torch.bfloat16 and qkv.is_contiguous()
     delta = torch.empty(tokens, num_heads, dtype=torch.float32, device=qkv.device)      # rowsum(dout o out), filled by the prologue kernel
     dqkv = torch.empty_like(qkv)
-    dq_part = torch.empty(4, tokens, d_model, dtype=torch.float32, device=qkv.device)   # one partial per 128-key block
+    dq_part = torch.empty(4, tokens, d_model, dtype=torch.bfloat16, device=qkv.device)  # one partial per 128-key block
     native.check(_lib().lah_attention_bwd(ptr(qkv), ptr(out), ptr(dout), ptr(lse), ptr(delta), ptr(dqkv), ptr(dq_part),
                                           tokens // 512, num_heads, d_model, stream_ptr()), "lah_attention_bwd")
     native.count_launch(3)   # delta prologue, tcgen05 backward, dQ partial reduction
