@@ -170,3 +170,23 @@ def test_lib_alias_exposes_the_reference_public_surface():
     assert lib.server.TesseractServer is lib.TesseractServer and lib.client.RemoteExpert is lib.RemoteExpert
     assert lib.network.HEARTBEAT_EXPIRATION == 120 and lib.network.UID_DELIMETER == "."
     assert lib.Connection.header_size == 4 and lib.Connection.payload_length_size == 8 and lib.DUMMY_BATCH_SIZE == 3
+
+
+def test_reference_module_paths_resolve():
+    """a user of the reference imports by ITS module paths (lib/utils/threading.py, experiments/convergence/dmoe_emulator.py,
+    ...): every one of them must resolve here"""
+    import importlib
+    import lah_b200  # noqa: F401  (installs the `lib` alias)
+    for name in ["lib.utils.connection", "lib.utils.data", "lib.utils.nested", "lib.utils.proto", "lib.utils.serializer",
+                 "lib.utils.shared_arrays", "lib.utils.shared_future", "lib.utils.threading", "lib.client.gating_function",
+                 "lib.client.remote_expert", "lib.runtime.expert_backend", "lib.runtime.task_pool",
+                 "lib.server.connection_handler", "lib.server.network_handler", "lib.network",
+                 "lah_b200.experiments.throughput.layers", "lah_b200.experiments.throughput.throughput_server",
+                 "lah_b200.experiments.throughput.throughput_client", "lah_b200.experiments.throughput.baseline_throughput",
+                 "lah_b200.experiments.throughput.rpc_throughput", "lah_b200.experiments.convergence.dmoe_emulator",
+                 "lah_b200.experiments.convergence.faulty_dmoe_emulator"]:
+        importlib.import_module(name)
+    from lib.utils.threading import run_and_await_k, CountdownEvent  # noqa: F401
+    from lah_b200.experiments.convergence.faulty_dmoe_emulator import EmulatedFaultyDMoE, get_non_expert_params  # noqa: F401
+    import threading as std_threading
+    assert hasattr(std_threading, "Thread")   # the alias module does not shadow the standard library
