@@ -31,6 +31,9 @@ def shadow_plan(counts: Sequence[Sequence[int]], E_loc: int, max_shadow: int, to
 
     Greedy, deterministic (ties -> smaller index): while the most loaded rank exceeds ``tol`` x the mean load, its largest
     not-yet-shadowed expert is shadowed, unless that expert has fewer than ``min_rows`` rows in total.
+    The greedy step always relieves the owner; it is not guaranteed to lower the maximum for adversarial count matrices (a
+    nearly-as-loaded sender that contributed most of the expert's rows gets them back) — with real routing every rank
+    contributes ~1/world of an expert's rows (tests/test_properties.py).
     """
     world, E = len(counts), len(counts[0])
     tot = [sum(counts[r][e] for r in range(world)) for e in range(E)]

@@ -101,9 +101,9 @@ def decode(buf) -> Tuple[str, Tuple[torch.Tensor, ...]]:
             t = torch.frombuffer(view[off: off + nbytes], dtype=carrier)
             if carrier != dtype:
                 t = t.view(dtype)
-            t = t.view(*dims)
+            t = t.view(tuple(dims))      # tuple form: a 0-dim tensor has dims == ()
         else:
-            t = torch.empty(*dims, dtype=dtype)
+            t = torch.empty(tuple(dims), dtype=dtype)
         off += nbytes
         out.append(t)
     return uid, tuple(out)
