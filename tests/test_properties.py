@@ -189,3 +189,56 @@ def test_adam_oracle_equals_torch_adam_per_group(G, sizes, steps, amsgrad, seed)
     for group, pviews in zip(params, views(p)):
         for t, pv in zip(group, pviews):
             assert torch.allclose(t.detach(), pv, atol=2e-6, rtol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------ server-side batching, k-of-n
+@settings(max_examples=40, deadline=None)
+@given(sizes=st.lists(st.integers(1, 6), min_size=1, max_size=12), max_batch=st.integers(1, 16))
+def test_task_pool_batches_preserve_order_and_rows(sizes, max_batch):
+    """dynamic batching (reference lib/runtime/task_pool.py:105-125): requests are served in submission order, a batch is a
+    prefix of the queue that stops with the first task that reaches max_batch_size (overshoot by at most one task), every row
+    comes back to the future of the request that sent it"""
+    from lah_b200.runtime import TaskPool
+    schema = (lah_b200.BatchTensorProto(2),)
+    pool = TaskPool(lambda x: (x + 1,), schema, schema, max_batch_size=max_batch, pool_size=len(sizes) + 1)
+    xs = [torch.full((n, 2), float(i)) for i, n in enumerate(sizes)]
+    futures = [pool.submit_task(x) for x in xs]
+    served = 0
+    while served < len(xs):
+        index, (batch,) = pool.load_batch_to_runtime(timeout=1)
+        rows, taken = 0, 0
+        while served + taken < len(xs) and rows < max_batch:      # greedy prefix: add tasks until the size is reached
+            rows += sizes[served + taken]
+            taken += 1
+        assert batch.shape[0] == rows and torch.equal(batch, torch.cat(xs[served: served + taken]))
+        pool.send_outputs_from_runtime(index, pool.process_func(batch))
+        served += taken
+    for fut, x in zip(futures, xs):
+        assert torch.equal(fut.result(timeout=1)[0], x + 1)
+    assert pool.empty
+
+
+@settings(max_examples=40, deadline=None)
+@given(outcomes=st.lists(st.booleans(), min_size=1, max_size=8), data=st.data())
+def test_run_and_await_k_returns_every_outcome_or_raises(outcomes, data):
+    """reference lib/utils/threading.py:76-125: with k successes available every job's outcome is reported (value or
+    exception); with fewer than k possible successes the call raises instead of hanging"""
+    from lah_b200.utils.threads import run_and_await_k
+    k = data.draw(st.integers(0, len(outcomes)))
+
+    def job(i, ok):
+        def run():
+            if not ok:
+                raise KeyError(i)
+            return i
+        return run
+
+    jobs = [job(i, ok) for i, ok in enumerate(outcomes)]
+    if sum(outcomes) >= k:
+        res = run_and_await_k(jobs, k, timeout_after_k=1.0, timeout_total=5.0)
+        assert len(res) == len(jobs)
+        for i, (ok, r) in enumerate(zip(outcomes, res)):
+            assert (r == i) if ok else isinstance(r, (KeyError, TimeoutError))
+    else:
+        with pytest.raises(ValueError):
+            run_and_await_k(jobs, k, timeout_after_k=1.0, timeout_total=5.0)
