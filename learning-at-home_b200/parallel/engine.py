@@ -86,8 +86,8 @@ class DMoEConfig:
     optimizer_ctas: int = -1
     # asynchronous expert updates (reference: EmulatedDMoE.update_every_inputs / update_every_steps,
     # experiments/convergence/dmoe_emulator.py:70-77): an expert accumulates weight gradients and steps once it has seen
-    # >= update_every_inputs rows or >= update_every_steps steps since its first pending row.  (0, 0) = step after every
-    # backward batch (lib/runtime/expert_backend.py:95-97), the default.
+    # >= update_every_inputs rows or >= update_every_steps steps since its first pending row (either suffices; a 0 leaves that
+    # clause unset).  (0, 0) = step after every backward batch (lib/runtime/expert_backend.py:95-97), the default.
     update_every_inputs: int = 0
     update_every_steps: int = 0
     # stale trainer gradients (reference notebooks, cell 3: a trainer computes the gradients of the non-expert parameters,
@@ -114,6 +114,13 @@ class DMoEConfig:
     @property
     def accumulate(self) -> bool:
         return self.update_every_inputs > 1 or self.update_every_steps > 1
+
+    def update_thresholds(self) -> Tuple[int, int]:
+        """(rows, steps) an expert must have pending to be stepped — either one suffices, like the reference's
+        ``inputs >= update_every_inputs or steps >= update_every_steps``; 0 leaves that clause unset (never fires on its own)"""
+        never = 2 ** 31 - 1
+        return (self.update_every_inputs if self.update_every_inputs > 0 else never,
+                self.update_every_steps if self.update_every_steps > 0 else never)
 
     @property
     def num_experts(self) -> int:
@@ -808,8 +815,8 @@ class FusedDMoE(nn.Module):
             # the expert has seen >= update_every_inputs rows or >= update_every_steps steps since its first pending row
             sh.pending_rows += ws.step_rows
             sh.pending_steps += (sh.pending_rows > 0).to(torch.int32)
-            due = (sh.pending_rows > 0) & ((sh.pending_rows >= max(1, cfg.update_every_inputs)) |
-                                           (sh.pending_steps >= max(1, cfg.update_every_steps)))
+            thr_rows, thr_steps = cfg.update_thresholds()
+            due = (sh.pending_rows > 0) & ((sh.pending_rows >= thr_rows) | (sh.pending_steps >= thr_steps))
             sh.fire.copy_(due.to(torch.int32))
             sh.pending_rows.mul_(1 - sh.fire)
             sh.pending_steps.mul_(1 - sh.fire)
@@ -843,18 +850,31 @@ class FusedDMoE(nn.Module):
         sh, cfg = self.shard, self.cfg
         if self._ref_rows is None:
             return
-        rows = self._ref_rows
-        sh.step += (rows > 0).to(sh.step.dtype)
+        rows, zero_mask = self._ref_rows, 0
         with torch.no_grad():
             for le, leaves in self._ref_leaves.items():   # gather the per-tensor gradients into the flat gradient buffer
                 for n, leaf in leaves.items():
-                    if leaf.grad is not None:
+                    if cfg.accumulate:                    # update_every_*: gradients pile up until the expert is due
+                        if leaf.grad is not None:
+                            sh.grads[n][le].add_(leaf.grad)
+                    elif leaf.grad is not None:
                         sh.grads[n][le].copy_(leaf.grad)
-                        leaf.grad = None
                     else:
                         sh.grads[n][le].zero_()
+                    leaf.grad = None
+            if cfg.accumulate:   # same bookkeeping as apply_expert_gradients (dmoe_emulator.py:70-77)
+                sh.pending_rows += rows.to(sh.pending_rows.dtype)
+                sh.pending_steps += (sh.pending_rows > 0).to(sh.pending_steps.dtype)
+                thr_rows, thr_steps = cfg.update_thresholds()
+                due = (sh.pending_rows > 0) & ((sh.pending_rows >= thr_rows) | (sh.pending_steps >= thr_steps))
+                keep = (~due).to(sh.pending_rows.dtype)
+                sh.pending_rows.mul_(keep)
+                sh.pending_steps.mul_(keep)
+                rows, zero_mask = due.to(rows.dtype), (1 << len(SEG_NAMES)) - 1
+            sh.step += (rows > 0).to(sh.step.dtype)
             K.adam_step_ref(sh.p, sh.g, sh.m, sh.v, sh.vmax, sh.seg_sizes, self.E_loc, step=sh.step,
-                            group_rows=rows, lr=cfg.lr, betas=cfg.betas, eps=cfg.eps, amsgrad=cfg.amsgrad)
+                            group_rows=rows, lr=cfg.lr, betas=cfg.betas, eps=cfg.eps, amsgrad=cfg.amsgrad,
+                            zero_mask=zero_mask)
         sh.sync_bf16()
         self._ref_rows = None
         self._ref_leaves = {}

@@ -420,7 +420,15 @@ class DMoETrainer:
                        max_exp_avg_sq=self.flat_vmax.detach().clone().cpu(), step=self.step_count)
         # the failure-injection stream position: device-side token base on GPU runs (csrc/moe.cu Peers::step_ctr)
         token_base = int(self.ctx.step_ctr[2:4].view(torch.int64).item()) if self.cuda else 0
-        return dict(trainer=trainer, experts=experts, rng=torch.get_rng_state(), token_base=token_base)
+        state = dict(trainer=trainer, experts=experts, rng=torch.get_rng_state(), token_base=token_base)
+        # what is IN FLIGHT in the asynchronous modes: the delay line of stale trainer gradients and, with update_every_*,
+        # every expert's pending row / step counters and its partially accumulated gradient (per rank, like `experts`)
+        if self._stale_ring is not None:
+            trainer["stale_ring"] = self._stale_ring.detach().clone().cpu()
+        if self.cfg.accumulate:
+            state["pending"] = [dict(rows=b.shard.pending_rows.clone().cpu(), steps=b.shard.pending_steps.clone().cpu(),
+                                     grad=b.shard.g.detach().clone().cpu()) for b in self.model.blocks]
+        return state
 
     def load_state_dict(self, state):
         from .engine import expert_uid
@@ -430,6 +438,12 @@ class DMoETrainer:
             self.flat_m.copy_(state["trainer"]["exp_avg"])
             self.flat_v.copy_(state["trainer"]["exp_avg_sq"])
             self.flat_vmax.copy_(state["trainer"]["max_exp_avg_sq"])
+            if self._stale_ring is not None and "stale_ring" in state["trainer"]:
+                self._stale_ring.copy_(state["trainer"]["stale_ring"])
+            for block, pend in zip(self.model.blocks, state.get("pending", [])):
+                block.shard.pending_rows.copy_(pend["rows"])
+                block.shard.pending_steps.copy_(pend["steps"])
+                block.shard.g.copy_(pend["grad"])
         self.step_count = int(state["trainer"]["step"])
         if self.cuda:
             self.step_dev.fill_(self.step_count)

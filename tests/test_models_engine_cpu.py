@@ -298,7 +298,7 @@ def test_fast_nccl_baseline_formulation_learns_on_cpu():
         assert losses[-1] < 0.6 * losses[0], losses
 
 
-def test_stale_trainer_gradients_and_update_every_on_cpu():
+def test_stale_trainer_gradients_on_cpu():
     """asynchrony knobs of the engine (reference: notebooks' delay_steps, dmoe_emulator.py:70-77)"""
     torch.manual_seed(0)
     cfg = E.DMoEConfig(hidden=32, grid_size=(2, 2), k=2, num_layers=1, in_features=12, tokens_per_rank=32, lr=3e-3,
@@ -314,6 +314,38 @@ def test_stale_trainer_gradients_and_update_every_on_cpu():
     assert not torch.equal(tr.model.head.weight, w0)      # ... the gradient of step 0 arrives with step 2
     losses = [tr.train_step(x, y) for _ in range(40)]
     assert losses[-1] < 0.7 * losses[0]
+
+
+def test_update_every_on_cpu_matches_the_emulator_schedule_and_resumes():
+    """DMoEConfig.update_every_inputs / update_every_steps on the CPU oracle path: experts accumulate gradients and step only
+    when due (dmoe_emulator.py:70-77; same schedule as the GPU test); the pending counters and the partially accumulated
+    gradient are part of the checkpoint"""
+    torch.manual_seed(0)
+    cfg = E.DMoEConfig(hidden=16, grid_size=(2, 2), k=4, num_layers=1, in_features=8, tokens_per_rank=16,
+                       update_every_inputs=10 ** 6, update_every_steps=3)
+    tr = DMoETrainer(cfg)
+    x, y = torch.randn(16, 8), torch.randint(0, 10, (16,))
+    steps, clone = [], None
+    for i in range(7):
+        tr.train_step(x, y)
+        steps.append(int(tr.model.blocks[0].shard.step.max()))
+        if i == 3:   # mid-accumulation: one pending step, a non-zero gradient buffer
+            state = tr.state_dict()
+            assert int(state["pending"][0]["steps"].max()) == 1 and float(state["pending"][0]["grad"].abs().sum()) > 0
+            clone = DMoETrainer(cfg)
+            clone.load_state_dict(state)
+    assert steps == [0, 0, 1, 1, 1, 2, 2], steps
+    for _ in range(3):
+        clone.train_step(x, y)
+    assert torch.allclose(clone.model.blocks[0].shard.p, tr.model.blocks[0].shard.p, atol=1e-6)
+    # update_every_inputs: 16 samples x top-4 of 4 experts = 16 rows per expert and step -> due every second step at 32
+    cfg2 = E.DMoEConfig(hidden=16, grid_size=(2, 2), k=4, num_layers=1, in_features=8, tokens_per_rank=16, update_every_inputs=32)
+    tr2 = DMoETrainer(cfg2)
+    seen = []
+    for _ in range(4):
+        tr2.train_step(x, y)
+        seen.append(int(tr2.model.blocks[0].shard.step.max()))
+    assert seen == [0, 1, 1, 2], seen
 
 
 def test_expert_path_selection():
