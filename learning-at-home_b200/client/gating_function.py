@@ -149,7 +149,9 @@ class GatingFunction(nn.Module):
     # ------------------------------------------------------------------ beam search over the product grid
     def beam_search(self, grid_scores: Sequence[torch.Tensor], k_best: int, **kwargs) -> List[List[RemoteExpert]]:
         """
-        Exact beam search over the grid with liveness filtering at every dimension.
+        Beam search (width k_best) over the grid with liveness filtering at every dimension, like the reference's.  With
+        additive scores it returns the exact top-k whenever liveness prunes nothing; with holes in the grid it is a heuristic
+        (a live prefix may win a level and have only poor descendants) — the fused in-box gate scores all alive experts.
         :param grid_scores: per grid dimension, a [batch, grid_size[d]] tensor of scores
         :returns: per sample, up to k_best alive RemoteExperts ordered by decreasing total score
         """
