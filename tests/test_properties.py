@@ -265,14 +265,19 @@ def test_cpu_trainer_any_configuration_steps_and_resumes(grid, k, layers, micro,
                        update_every_steps=every[1], gate_mode=gate, failure_rate=fail, seed=3)
     torch.manual_seed(1)
     x, y = torch.randn(16, 8), torch.randint(0, 10, (16,))
-    trainer = DMoETrainer(cfg)
-    losses = [trainer.train_step(x, y) for _ in range(3)]
-    assert all(l == l and abs(l) < 1e4 for l in losses), losses
-    if fail == 0.0:   # (failure masks are drawn from the global RNG on the oracle path: only the deterministic runs are compared)
-        clone = DMoETrainer(cfg)
-        clone.load_state_dict(trainer.state_dict())
-        for _ in range(2):
-            assert abs(trainer.train_step(x, y) - clone.train_step(x, y)) < 1e-5
+    threads = torch.get_num_threads()
+    torch.set_num_threads(1)   # tiny tensors: intra-op threads only fight the background threads earlier tests left behind
+    try:
+        trainer = DMoETrainer(cfg)
+        losses = [trainer.train_step(x, y) for _ in range(3)]
+        assert all(l == l and abs(l) < 1e4 for l in losses), losses
+        if fail == 0.0:   # (failure masks come from the global RNG on the oracle path: only deterministic runs are compared)
+            clone = DMoETrainer(cfg)
+            clone.load_state_dict(trainer.state_dict())
+            for _ in range(2):
+                assert abs(trainer.train_step(x, y) - clone.train_step(x, y)) < 1e-5
+    finally:
+        torch.set_num_threads(threads)
 
 
 # ------------------------------------------------------------------------------------------------ expert index + beam search
