@@ -57,12 +57,18 @@ class Connection(AbstractContextManager):
             self.conn.sendall(part)
 
     # ---------------------------------------------------------------- receive
+    #: payloads up to this size are received into one pre-sized buffer; larger ones grow the buffer (doubling) as the bytes
+    #: actually ARRIVE, so a peer that merely announces gigabytes cannot make this process allocate them
+    eager_alloc = 64 << 20
+
     def _recv_exact(self, nbytes: int) -> bytearray:
-        buf = bytearray(nbytes)
-        view = memoryview(buf)
+        buf = bytearray(min(nbytes, self.eager_alloc))
         got = 0
         while got < nbytes:
-            n = self.conn.recv_into(view[got:], nbytes - got)
+            if got == len(buf):                                   # large message: the announced bytes keep coming -> grow
+                buf.extend(bytes(min(nbytes - got, len(buf))))
+            with memoryview(buf) as view:                         # (released before the next extend: no exported buffer)
+                n = self.conn.recv_into(view[got:], len(buf) - got)
             if n == 0:
                 raise RuntimeError("socket connection broken")
             got += n

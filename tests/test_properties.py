@@ -317,3 +317,52 @@ def test_index_and_beam_search_agree_with_brute_force(grid, k, batch, data):
         # own score and then have only poor descendants (hypothesis: grid [3, 1, 4], k = 1, two far-apart alive experts).
         # The fused gate (gate_topk_kernel / gate_topk_ref) scores all alive experts and IS exact — tested above.
     gate.close()
+
+
+# ------------------------------------------------------------------------------------------------ TCP framing
+@settings(max_examples=25, deadline=None)
+@given(header=st.text(alphabet="abcdefghijklmnopqrstuvwxyz_", min_size=4, max_size=4), payload=st.binary(max_size=5000),
+       chunk=st.integers(1, 700), eager=st.sampled_from([16, 1000, 64 << 20]))
+def test_connection_framing_with_arbitrary_fragmentation(header, payload, chunk, eager):
+    """header(4) | length(8, big endian) | payload (reference lib/utils/connection.py): the receiver reassembles a message that
+    arrives in arbitrary fragments, whether the buffer was pre-sized or grown as the bytes arrived"""
+    import socket
+    import threading
+    from lah_b200.utils.connection import Connection
+    a, b = socket.socketpair()
+    rx = Connection(b, ("local", 0))
+    rx.eager_alloc = eager
+    wire = header.encode() + len(payload).to_bytes(8, "big") + payload
+
+    def feed():
+        for i in range(0, len(wire), chunk):
+            a.sendall(wire[i: i + chunk])
+
+    t = threading.Thread(target=feed)
+    t.start()
+    try:
+        assert rx.recv_message() == (header, payload)
+    finally:
+        t.join()
+        a.close()
+        rx.close()
+
+
+def test_connection_does_not_allocate_what_a_peer_merely_announces():
+    import socket
+    from lah_b200.utils.connection import Connection
+    a, b = socket.socketpair()
+    rx = Connection(b, ("local", 0))
+    a.sendall(b"fwd_" + (3 << 30).to_bytes(8, "big") + b"x" * 10)   # announces 3 GiB, sends 10 bytes, hangs up
+    a.close()
+    assert rx.recv_header() == "fwd_"
+    with pytest.raises(RuntimeError):
+        rx.recv_raw()
+    rx.close()
+    a2, b2 = socket.socketpair()
+    rx2 = Connection(b2, ("local", 0))
+    a2.sendall(b"fwd_" + (1 << 40).to_bytes(8, "big"))             # beyond max_payload: refused before any allocation
+    assert rx2.recv_header() == "fwd_"
+    with pytest.raises(ValueError):
+        rx2.recv_raw()
+    a2.close(), rx2.close()
