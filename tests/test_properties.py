@@ -366,3 +366,55 @@ def test_connection_does_not_allocate_what_a_peer_merely_announces():
     with pytest.raises(ValueError):
         rx2.recv_raw()
     a2.close(), rx2.close()
+
+
+# ------------------------------------------------------------------------------------------------ live server under fuzz
+@pytest.fixture(scope="module")
+def fuzz_server():
+    from lah_b200.models import FeedforwardBlock
+    expert = FeedforwardBlock(16)
+    backend = lah_b200.ExpertBackend(name="e", expert=expert, opt=torch.optim.Adam(expert.parameters(), lr=1e-3),
+                                     args_schema=(lah_b200.BatchTensorProto(16),), outputs_schema=lah_b200.BatchTensorProto(16),
+                                     max_batch_size=64)
+    srv = lah_b200.TesseractServer(None, {"e": backend}, port=0, conn_handler_processes=1)   # ONE acceptor
+    srv.run_in_background()
+    yield srv
+    srv.shutdown()
+
+
+pickled = st.recursive(st.one_of(st.none(), st.integers(-5, 5), st.text(max_size=5), st.binary(max_size=8)),
+                       lambda kids: st.one_of(st.lists(kids, max_size=3), st.tuples(kids, kids)), max_leaves=6)
+
+
+@settings(max_examples=25, deadline=None, suppress_health_check=list(hypothesis.HealthCheck))
+@given(header=st.sampled_from(["fwd_", "bwd_", "info", "fwdT", "bwdT", "zzzz", "rest"]), body=st.binary(max_size=300),
+       obj=pickled, lie=st.integers(0, 400))
+def test_server_survives_arbitrary_requests(fuzz_server, header, body, obj, lie):
+    """raw garbage, a lying length prefix and well-formed pickles of the wrong shape, on every request type: each costs its
+    author an error reply or the connection; the single acceptor and the runtime keep serving a correct client"""
+    import socket
+    from lah_b200.utils import Connection, PytorchSerializer
+    port = fuzz_server.port
+
+    def raw(payload: bytes):
+        with socket.create_connection(("127.0.0.1", port), timeout=5) as s:
+            s.sendall(payload)
+            s.settimeout(0.3)
+            try:
+                s.recv(1 << 16)
+            except (socket.timeout, ConnectionResetError, BrokenPipeError):
+                pass
+
+    raw(header.encode() + len(body).to_bytes(8, "big") + body)
+    raw(header.encode() + lie.to_bytes(8, "big") + body[: max(0, lie - 1)])            # announces more than it sends
+    with Connection.create("127.0.0.1", port, timeout=5) as c:
+        c.send_raw(header, PytorchSerializer.dumps(("e", obj)))
+        c.conn.settimeout(2)
+        try:
+            reply, _ = c.recv_message()
+            assert reply in ("err_", "rest", "resT")
+        except (socket.timeout, RuntimeError, ConnectionResetError):
+            pass
+    remote = lah_b200.RemoteExpert("e", "127.0.0.1", port, timeout=10)
+    x = torch.randn(3, 16)
+    assert torch.allclose(remote(x), fuzz_server.experts["e"].expert(x), atol=1e-5)
