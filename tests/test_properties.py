@@ -418,3 +418,19 @@ def test_server_survives_arbitrary_requests(fuzz_server, header, body, obj, lie)
     remote = lah_b200.RemoteExpert("e", "127.0.0.1", port, timeout=10)
     x = torch.randn(3, 16)
     assert torch.allclose(remote(x), fuzz_server.experts["e"].expert(x), atol=1e-5)
+
+
+def test_expert_index_grows_and_keeps_every_entry():
+    """native open-addressing index (csrc/host_runtime.cpp): 20,000 experts + their prefixes force several rehashes; every
+    declared uid stays retrievable with its (owner, slot), absent uids stay absent, a re-declaration overwrites in place"""
+    import lah_b200 as lib
+    net = lib.InBoxNetwork()
+    uids = [f"big.{i // 200}.{i % 200}" for i in range(20000)]
+    net.declare_experts(uids, "127.0.0.1", 1, owner=3, slots=list(range(20000)))
+    for i in (0, 1, 199, 200, 7777, 19999):
+        assert net._fresh("expert", uids[i], 60.0) == (3, i)
+    assert all(e is not None for e in net.get_experts(uids[::97]))
+    assert net.get_experts(["big.100.200", "big.9999.0", "bigger.0.0"]) == [None, None, None]
+    assert net.first_k_active(["big.500", "big.42", "big.99"], 2) == ["big.42", "big.99"]
+    net.declare_experts([uids[5]], "127.0.0.1", 1, owner=1, slots=[9])
+    assert net._fresh("expert", uids[5], 60.0) == (1, 9)
