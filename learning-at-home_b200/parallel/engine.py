@@ -108,8 +108,10 @@ class DMoEConfig:
         if self.expert_path != "auto":
             return self.expert_path
         rows_per_expert = self.tokens_per_rank * world * self.k / max(1, self.num_experts)
+        experts_per_rank = -(-self.num_experts // max(1, world))
         return "small" if (rows_per_expert < 512 and self.expert_dtype == "bf16" and self.inner % 128 == 0
-                           and self.hidden % 128 == 0) else "big"
+                           and self.hidden % 128 == 0
+                           and experts_per_rank <= 1023) else "big"   # swap-AB keeps a per-group prefix table in smem (MAX_G)
 
     @property
     def accumulate(self) -> bool:

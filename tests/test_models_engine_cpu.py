@@ -357,6 +357,8 @@ def test_expert_path_selection():
     assert E.DMoEConfig(hidden=512, grid_size=(64,), k=4, tokens_per_rank=256, update_every_steps=3).resolved_path(1) == "big"
     assert E.DMoEConfig(hidden=512, grid_size=(64,), k=4, tokens_per_rank=256, expert_dtype="fp8").resolved_path(1) == "big"
     assert E.DMoEConfig(hidden=512, grid_size=(64,), k=4, tokens_per_rank=256, expert_path="big").resolved_path(1) == "big"
+    many = E.DMoEConfig(hidden=512, grid_size=(4096,), k=4, tokens_per_rank=512)     # swap-AB handles <= 1023 groups per rank
+    assert many.resolved_path(2) == "big" and many.resolved_path(8) == "small"
 
 
 def test_trainer_microbatches_step_experts_per_microbatch():
